@@ -1,0 +1,211 @@
+/*
+ * pbf_cuda.h — C ABI of the B200-native (sm_100a) Position-Based-Fluids step.
+ *
+ * This is the drop-in boundary for ONE path of UoB-HPC/pbf-sph: sph::Solver::advance
+ * (reference src/sph.hpp:119-125), i.e. the per-step PBF solve that the reference implements in
+ * src/omp/ompsph.hpp:85-485 (OpenMP), src/ocl/oclsph.cpp:315-513 (OpenCL) and src/sycl/syclsph.hpp.
+ * The C++ adaptor in include/pbf/cudasph.hpp wraps these entry points behind the reference's own
+ * `sph::Solver<size_t,float,V>` interface; INTEGRATION.md shows the `case Impl::CUDA` a maintainer adds
+ * beside src/benchmark.cpp:151.
+ *
+ * Plain pointers and sizes only.  Every function returns PBF_OK (0) or a negative pbf_status; the
+ * message is available from pbf_last_error().  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with PBF_ERR_CUDA.
+ */
+#ifndef PBF_CUDA_H
+#define PBF_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBF_ABI_VERSION 1
+
+typedef enum pbf_status {
+  PBF_OK = 0,
+  PBF_ERR_INVALID = -1,     /* bad argument (NULL, Obstacle particle, grid extent > 1023 cells, ...) */
+  PBF_ERR_CUDA = -2,        /* CUDA runtime/driver error, or no device */
+  PBF_ERR_NCCL = -3,        /* NCCL error */
+  PBF_ERR_STATE = -4,       /* call order (e.g. step before upload) */
+  PBF_ERR_CAPACITY = -5     /* a caller-provided buffer is too small */
+} pbf_status;
+
+/* sph::Type — src/sph.hpp:15.  Only Fluid is accepted (SURVEY note O: the OMP backend drops Obstacles). */
+enum { PBF_TYPE_FLUID = 0, PBF_TYPE_OBSTACLE = 1 };
+
+/* sph::Particle<size_t,float,glm::vec> — src/sph.hpp:36-54.  56 bytes, 8-aligned:
+ * id@0 type@8 mass@12 position@16 velocity@28 colour@40.  This is what crosses advance(). */
+typedef struct pbf_particle {
+  uint64_t id;
+  uint8_t type;
+  uint8_t _pad[3];
+  float mass;
+  float position[3];
+  float velocity[3];
+  float colour[4];
+} pbf_particle;
+
+/* sph::McParams<float> — src/sph.hpp:82-95 */
+typedef struct pbf_mc_params {
+  float resolution;
+  float isolevel;
+  float particle_size;
+  float particle_influence;
+} pbf_mc_params;
+
+/* sph::SphParams<size_t,float,V> — src/sph.hpp:97-103.  `h` is omitted on purpose: no reference solver
+ * reads SphParams::h, the smoothing length is the solver's constructor argument (ompsph.hpp:80-83). */
+typedef struct pbf_params {
+  float dt;
+  float scale;
+  uint64_t iteration;
+  float constant_force[3];
+  float min_bound[3];
+  float max_bound[3];
+  int32_t wait;            /* SphParams::wait — "synchronise"; the host-vector contract always syncs */
+  int32_t surface_enabled; /* std::optional<McParams>::has_value() */
+  pbf_mc_params surface;
+} pbf_params;
+
+/* Grid derived once per step — ompsph.hpp:132-135 and sph.hpp:238-241. */
+typedef struct pbf_grid_info {
+  float min_extent[3];
+  uint32_t extent[3];      /* cells per axis */
+  uint32_t grid_table_n;   /* G = morton(extent) = size of the cell table */
+  uint32_t key_bits;       /* bit_length(G-1) */
+  uint32_t radix_passes;   /* LSD passes actually run */
+  uint64_t n_particles;
+  uint32_t sample_size[3]; /* MC lattice points per axis (0 when surface disabled) */
+  uint32_t n_triangles;    /* triangles emitted by the last step (0 when surface disabled) */
+} pbf_grid_info;
+
+/* Behaviour flags (pbf_set_flags).  Defaults: 0. */
+enum {
+  PBF_FLAG_STRICT_FP = 1u << 0,    /* no FMA contraction, IEEE div/sqrt in the solver kernels: follows the oracle op-for-op */
+  PBF_FLAG_DEBUG_COUNTS = 1u << 1, /* also run the neighbour-count tap each step (PBF_TAP_CAND_COUNT/NBR_COUNT) */
+  PBF_FLAG_PROFILE = 1u << 2,      /* record CUDA events around every kernel family (pbf_profile_read) */
+  PBF_FLAG_GLOBAL_NEIGHBOURS = 1u << 3 /* use the un-tiled global-memory neighbour kernels (A/B testing) */
+};
+
+/* Debug taps, all in SORTED particle order unless stated (pbf_debug_read). */
+typedef enum pbf_tap {
+  PBF_TAP_KEYS_INPUT = 0,  /* u32[n]  Morton key per particle, INPUT order (ompsph.hpp:152) */
+  PBF_TAP_PERM = 1,        /* u32[n]  sorted position -> input index (stable sort, ompsph.hpp:158) */
+  PBF_TAP_KEYS_SORTED = 2, /* u32[n] */
+  PBF_TAP_CELL_TABLE = 3,  /* u32[G]  sph.hpp:238-250 */
+  PBF_TAP_CAND_COUNT = 4,  /* u32[n]  27-cell candidates incl. self, on the predicted positions */
+  PBF_TAP_NBR_COUNT = 5,   /* u32[n]  candidates with r <= h incl. self */
+  PBF_TAP_LAMBDA = 6,      /* f32[n]  lambda of the LAST solver iteration (ompsph.hpp:231) */
+  PBF_TAP_RHO = 7,         /* f32[n]  density of the LAST solver iteration (ompsph.hpp:227) */
+  PBF_TAP_IDS = 8,         /* u64[n] */
+  PBF_TAP_MC_FIELD = 9,    /* f32[4*L] lattice (value, normal.xyz), index3d order (ompsph.hpp:350-354) */
+  PBF_TAP_MC_COLOUR = 10   /* f32[4*L] lattice colour (ompsph.hpp:355) */
+} pbf_tap;
+
+/* Kernel families timed under PBF_FLAG_PROFILE.  ms are accumulated since the last pbf_profile_reset. */
+enum {
+  PBF_PH_PREDICT_KEY = 0,
+  PBF_PH_SORT = 1,
+  PBF_PH_REORDER = 2,
+  PBF_PH_CELL_TABLE = 3,
+  PBF_PH_DIFFUSE = 4,
+  PBF_PH_LAMBDA = 5,
+  PBF_PH_DELTA = 6,
+  PBF_PH_FINALISE = 7,
+  PBF_PH_MC_FIELD = 8,
+  PBF_PH_MC_COUNT_SCAN = 9,
+  PBF_PH_MC_EMIT = 10,
+  PBF_PH_PACK = 11,
+  PBF_PH_HALO = 12,
+  PBF_PH_COUNT = 16
+};
+typedef struct pbf_profile {
+  double ms[PBF_PH_COUNT];
+  uint64_t launches[PBF_PH_COUNT];
+  uint64_t steps;
+} pbf_profile;
+
+typedef struct pbf_ctx pbf_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Replaces the backend constructors the drivers call: omp_impl::Solver(h) benchmark.cpp:160-163,
+ * ocl_impl::Solver(h, kernelPath, includes, device) oclsph.hpp:145-148.  `device` = CUDA ordinal. */
+int pbf_create(pbf_ctx **out, float h, int device);
+void pbf_destroy(pbf_ctx *ctx);
+/* Message of the last failure on `ctx` (or of the last failed pbf_create when ctx == NULL). */
+const char *pbf_last_error(const pbf_ctx *ctx);
+int pbf_abi_version(void);
+int pbf_set_flags(pbf_ctx *ctx, uint32_t flags);
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int pbf_set_stream(pbf_ctx *ctx, void *cuda_stream);
+
+/* ---- drop-in path: sph::Solver::advance (sph.hpp:122-124) ------------------------------------ */
+/* H2D of xs, one PBF step, D2H.  On return xs[0..n) holds the advanced particles in Z-SORTED order
+ * (ompsph.hpp:479-481).  *n_mesh_vertices (may be NULL) receives 3*triangles when params->surface_enabled;
+ * fetch the mesh with pbf_mesh_download.  n == 0 is PBF_OK and does nothing (ompsph.hpp:122-126). */
+int pbf_advance_host(pbf_ctx *ctx, const pbf_params *params, pbf_particle *xs, uint64_t n,
+                     uint64_t *n_mesh_vertices);
+/* sph::ColouredMesh (sph.hpp:105-112): vs/ns = 3 floats per vertex, cs = 4 floats per vertex,
+ * non-indexed, triangles ordered by marching-cube index.  Each pointer may be NULL to skip it. */
+int pbf_mesh_download(pbf_ctx *ctx, float *vs, float *ns, float *cs, uint64_t capacity_vertices);
+
+/* ---- resident path (no host round trip between steps) ------------------------------------------ */
+int pbf_upload(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n);
+int pbf_step(pbf_ctx *ctx, const pbf_params *params);          /* enqueue one step (asynchronous) */
+int pbf_sync(pbf_ctx *ctx);
+int pbf_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_t *n_out);
+int pbf_particle_count(pbf_ctx *ctx, uint64_t *n_out);
+/* Device pointers of the resident SoA state (float4 pos|mass, float4 vel, float4 colour, u64 id). */
+int pbf_device_state(pbf_ctx *ctx, void **pos4, void **vel4, void **col4, void **ids);
+
+/* ---- introspection for parity tests and the bench ------------------------------------------------ */
+int pbf_grid(pbf_ctx *ctx, pbf_grid_info *out);
+int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes);
+int pbf_profile_reset(pbf_ctx *ctx);
+int pbf_profile_read(pbf_ctx *ctx, pbf_profile *out);
+/* Number of kernel launches issued by this context since creation. */
+uint64_t pbf_launch_count(const pbf_ctx *ctx);
+
+/* ---- multi-GPU: Z-curve slab decomposition, one process (rank) per GPU ----------------------------- */
+/* The reference is single-device; this is the north-star extension.  Rank r owns the
+ * Morton key range [split[r], split[r+1]).  Ghost/migrant exchange uses ncclSend/ncclRecv. */
+#define PBF_NCCL_ID_BYTES 128
+int pbf_dist_unique_id(uint8_t id[PBF_NCCL_ID_BYTES]);
+int pbf_dist_init(pbf_ctx *ctx, const uint8_t id[PBF_NCCL_ID_BYTES], int rank, int world);
+/* Scatter-free start: every rank passes the FULL initial particle set; each keeps what it owns. */
+int pbf_dist_upload(pbf_ctx *ctx, const pbf_params *params, const pbf_particle *xs, uint64_t n);
+int pbf_dist_step(pbf_ctx *ctx, const pbf_params *params);
+/* Owned particles of this rank, Z-sorted. */
+int pbf_dist_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_t *n_out);
+typedef struct pbf_dist_stats {
+  uint64_t owned, ghosts, migrants_out, migrants_in;
+  uint64_t halo_bytes_per_iteration;
+  uint32_t key_lo, key_hi;
+} pbf_dist_stats;
+int pbf_dist_stats_read(pbf_ctx *ctx, pbf_dist_stats *out);
+
+/* ---- host-only helpers (no GPU needed; used by the CPU tests of the host logic) ------------------ */
+/* Grid set-up exactly as ompsph.hpp:132-135 / sph.hpp:240. */
+int pbf_host_grid(float h, const pbf_params *params, pbf_grid_info *out);
+/* Split the key space [0,G) into `world` contiguous ranges of ~equal particle count from a histogram
+ * over coarse key buckets (bucket b covers keys [b<<shift, (b+1)<<shift)).  splits has world+1 entries. */
+int pbf_host_plan_splits(const uint64_t *bucket_hist, uint32_t n_buckets, uint32_t shift, int world,
+                         uint32_t *splits);
+/* 10-bit-per-axis Morton encode/decode — src/curves.h:46-88. */
+uint32_t pbf_host_morton_encode(uint32_t x, uint32_t y, uint32_t z);
+void pbf_host_morton_decode(uint32_t key, uint32_t xyz[3]);
+
+#ifdef __cplusplus
+}
+#endif
+
+#ifdef __cplusplus
+static_assert(sizeof(pbf_particle) == 56, "must match sizeof(sph::Particle<size_t,float,glm::vec>)");
+#else
+_Static_assert(sizeof(pbf_particle) == 56, "must match sizeof(sph::Particle<size_t,float,glm::vec>)");
+#endif
+
+#endif /* PBF_CUDA_H */

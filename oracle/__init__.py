@@ -1,0 +1,219 @@
+"""ctypes binding of the CPU checker (TEST INFRASTRUCTURE — never imported by the product package).
+
+``liboracle.so``            oracle/pbf_oracle.c, the C restatement of ompsph.hpp:85-485
+``_ref/libpbf_ref_*.so``    the unmodified reference OpenMP backend (oracle/ref/ref_driver.cpp), built in
+                            the container that has /root/reference and shipped prebuilt to the GPU box.
+
+Allowed importers: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline / --impl reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+
+PARTICLE = np.dtype(
+    [("id", "<u8"), ("type", "u1"), ("_pad", "u1", (3,)), ("mass", "<f4"), ("position", "<f4", (3,)),
+     ("velocity", "<f4", (3,)), ("colour", "<f4", (4,))]
+)
+assert PARTICLE.itemsize == 56
+
+GAUSS_SEIDEL = 1
+SKIP_DIFFUSE = 2
+
+
+class McParams(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("isolevel", C.c_float), ("particle_size", C.c_float),
+                ("particle_influence", C.c_float)]
+
+
+class Params(C.Structure):
+    _fields_ = [("dt", C.c_float), ("scale", C.c_float), ("iteration", C.c_uint64),
+                ("constant_force", C.c_float * 3), ("min_bound", C.c_float * 3), ("max_bound", C.c_float * 3),
+                ("wait", C.c_int32), ("surface_enabled", C.c_int32), ("surface", McParams)]
+
+    def copy(self) -> "Params":
+        out = Params()
+        C.memmove(C.byref(out), C.byref(self), C.sizeof(Params))
+        return out
+
+
+class GridInfo(C.Structure):
+    _fields_ = [("min_extent", C.c_float * 3), ("extent", C.c_uint32 * 3), ("grid_table_n", C.c_uint32),
+                ("key_bits", C.c_uint32), ("radix_passes", C.c_uint32), ("n_particles", C.c_uint64),
+                ("sample_size", C.c_uint32 * 3), ("n_triangles", C.c_uint32)]
+
+
+class OracleIO(C.Structure):
+    _fields_ = [("keys_input", C.c_void_p), ("perm", C.c_void_p), ("keys_sorted", C.c_void_p),
+                ("cell_table", C.c_void_p), ("cell_table_cap", C.c_uint64),
+                ("cand_count", C.c_void_p), ("nbr_count", C.c_void_p), ("lambda_", C.c_void_p), ("rho", C.c_void_p),
+                ("mc_field", C.c_void_p), ("mc_colour", C.c_void_p), ("mc_lattice_cap", C.c_uint64),
+                ("mesh_vs", C.c_void_p), ("mesh_ns", C.c_void_p), ("mesh_cs", C.c_void_p),
+                ("mesh_cap_vertices", C.c_uint64), ("forced_perm", C.c_void_p),
+                ("grid", GridInfo), ("n_vertices", C.c_uint64)]
+
+
+def build(verbose: bool = False) -> None:
+    """Compile liboracle.so (and oracle/_ref when /root/reference exists).  Building is not using."""
+    subprocess.run(["make", "-C", str(HERE), "-j8"], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL, stderr=None if verbose else subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = HERE / "liboracle.so"
+        if not path.exists():
+            build()
+        _lib = C.CDLL(str(path))
+        _lib.pbf_oracle_step.argtypes = [C.c_float, C.POINTER(Params), C.c_void_p, C.c_uint64, C.c_uint32,
+                                         C.POINTER(OracleIO)]
+        _lib.pbf_oracle_step.restype = C.c_int
+        _lib.pbf_oracle_grid.argtypes = [C.c_float, C.POINTER(Params), C.POINTER(GridInfo)]
+        _lib.pbf_oracle_morton_encode.argtypes = [C.c_uint32] * 3
+        _lib.pbf_oracle_morton_encode.restype = C.c_uint32
+    return _lib
+
+
+def grid(h: float, params: Params) -> GridInfo:
+    g = GridInfo()
+    lib().pbf_oracle_grid(C.c_float(h), C.byref(params), C.byref(g))
+    return g
+
+
+def step(h: float, params: Params, xs: np.ndarray, mode: int = 0, taps: bool = False, mesh: bool = True,
+         forced_perm: np.ndarray | None = None) -> dict:
+    """One oracle step.  ``xs`` (PARTICLE array) is advanced IN PLACE into Z-sorted order.
+
+    Returns a dict with the grid info and, when ``taps``, every intermediate the parity tests compare."""
+    assert xs.dtype == PARTICLE and xs.flags.c_contiguous
+    n = len(xs)
+    g = grid(h, params)
+    io = OracleIO()
+    keep = {}
+
+    def buf(name, shape, dtype):
+        a = np.zeros(shape, dtype=dtype)
+        keep[name] = a
+        return a.ctypes.data
+
+    if taps:
+        io.keys_input = buf("keys_input", n, np.uint32)
+        io.perm = buf("perm", n, np.uint32)
+        io.keys_sorted = buf("keys_sorted", n, np.uint32)
+        io.cell_table = buf("cell_table", g.grid_table_n, np.uint32)
+        io.cell_table_cap = g.grid_table_n
+        io.cand_count = buf("cand_count", n, np.uint32)
+        io.nbr_count = buf("nbr_count", n, np.uint32)
+        io.lambda_ = buf("lambda", n, np.float32)
+        io.rho = buf("rho", n, np.float32)
+    if params.surface_enabled:
+        L = int(g.sample_size[0]) * int(g.sample_size[1]) * int(g.sample_size[2])
+        if taps:
+            io.mc_field = buf("mc_field", (L, 4), np.float32)
+            io.mc_colour = buf("mc_colour", (L, 4), np.float32)
+            io.mc_lattice_cap = L
+        if mesh:
+            cap = 15 * max(1, (int(g.sample_size[0]) - 1) * (int(g.sample_size[1]) - 1) * (int(g.sample_size[2]) - 1))
+            cap = min(cap, 6_000_000)
+            io.mesh_vs = buf("mesh_vs", (cap, 3), np.float32)
+            io.mesh_ns = buf("mesh_ns", (cap, 3), np.float32)
+            io.mesh_cs = buf("mesh_cs", (cap, 4), np.float32)
+            io.mesh_cap_vertices = cap
+    if forced_perm is not None:
+        fp = np.ascontiguousarray(forced_perm, dtype=np.uint32)
+        keep["_forced"] = fp
+        io.forced_perm = fp.ctypes.data
+    rc = lib().pbf_oracle_step(C.c_float(h), C.byref(params), xs.ctypes.data, n, mode, C.byref(io))
+    if rc != 0:
+        raise RuntimeError(f"pbf_oracle_step failed: {rc}")
+    out = {k: v for k, v in keep.items() if not k.startswith("_")}
+    nv = int(io.n_vertices)
+    for k in ("mesh_vs", "mesh_ns", "mesh_cs"):
+        if k in out:
+            out[k] = out[k][:nv]
+    out["n_vertices"] = nv
+    out["grid"] = io.grid
+    return out
+
+
+# ---------------------------------------------------------------- the real reference (oracle/_ref)
+_ref = {}
+
+
+def ref_available(variant: str = "strict") -> bool:
+    return (HERE / "_ref" / f"libpbf_ref_{variant}.so").exists()
+
+
+def ref_lib(variant: str = "strict") -> C.CDLL:
+    """variant: strict | strict_stable | fast | native | best (native when this CPU has its ISA, else fast)."""
+    if variant == "best":
+        variant = "fast"
+        flags_file = HERE / "_ref" / "native_cpu_flags.txt"
+        if flags_file.exists() and (HERE / "_ref" / "libpbf_ref_native.so").exists():
+            need = set(flags_file.read_text().split())
+            have = set()
+            for line in open("/proc/cpuinfo"):
+                if line.startswith("flags"):
+                    have = set(line.split(":", 1)[1].split())
+                    break
+            if need <= have:
+                variant = "native"
+    if variant not in _ref:
+        path = HERE / "_ref" / f"libpbf_ref_{variant}.so"
+        L = C.CDLL(str(path))
+        L.pbf_ref_advance.argtypes = [C.c_float, C.POINTER(Params), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.pbf_ref_advance.restype = C.c_int
+        L.pbf_ref_variant.restype = C.c_char_p
+        L.pbf_ref_scene_2cubes.argtypes = [C.c_uint64, C.c_uint64, C.c_float, C.POINTER(Params), C.c_void_p, C.c_uint64]
+        L.pbf_ref_scene_2cubes.restype = C.c_uint64
+        L.pbf_ref_apply_motion.argtypes = [C.POINTER(Params), C.c_uint64, C.POINTER(Params)]
+        L.pbf_ref_morton_encode.argtypes = [C.c_uint32] * 3
+        L.pbf_ref_morton_encode.restype = C.c_uint32
+        L.pbf_ref_set_threads.argtypes = [C.c_int]
+        L.variant_name = variant
+        _ref[variant] = L
+    return _ref[variant]
+
+
+def ref_advance(h: float, params: Params, xs: np.ndarray, variant: str = "strict", threads: int | None = None,
+                mesh_cap: int = 0) -> dict:
+    """sph::omp_impl::Solver<size_t,float>(h).advance(params, {}, xs) on the real reference; xs in place."""
+    L = ref_lib(variant)
+    if threads is not None:
+        L.pbf_ref_set_threads(threads)
+    nv = C.c_uint64(0)
+    vs = np.zeros((mesh_cap, 3), np.float32)
+    ns = np.zeros((mesh_cap, 3), np.float32)
+    cs = np.zeros((mesh_cap, 4), np.float32)
+    rc = L.pbf_ref_advance(C.c_float(h), C.byref(params), xs.ctypes.data, len(xs), vs.ctypes.data, ns.ctypes.data,
+                           cs.ctypes.data, mesh_cap, C.byref(nv))
+    if rc != 0:
+        raise RuntimeError(f"pbf_ref_advance failed: {rc}")
+    k = min(int(nv.value), mesh_cap)
+    return {"n_vertices": int(nv.value), "mesh_vs": vs[:k], "mesh_ns": ns[:k], "mesh_cs": cs[:k]}
+
+
+def ref_scene_2cubes(count: int, solver_iter: int, scaling: float = 500.0, variant: str = "strict"):
+    L = ref_lib(variant)
+    p = Params()
+    n = L.pbf_ref_scene_2cubes(count, solver_iter, C.c_float(scaling), C.byref(p), None, 0)
+    xs = np.zeros(n, PARTICLE)
+    L.pbf_ref_scene_2cubes(count, solver_iter, C.c_float(scaling), C.byref(p), xs.ctypes.data, n)
+    return p, xs
+
+
+def ref_apply_motion(params: Params, frame: int, variant: str = "strict") -> Params:
+    out = Params()
+    ref_lib(variant).pbf_ref_apply_motion(C.byref(params), frame, C.byref(out))
+    return out
