@@ -187,6 +187,10 @@ typedef struct pbf_dist_stats {
 } pbf_dist_stats;
 int pbf_dist_stats_read(pbf_ctx *ctx, pbf_dist_stats *out);
 
+/* Pinned host memory for callers that want truly asynchronous H2D/D2H on the drop-in path. */
+void *pbf_host_alloc(uint64_t bytes);
+void pbf_host_free(void *p);
+
 /* ---- host-only helpers (no GPU needed; used by the CPU tests of the host logic) ------------------ */
 /* Grid set-up exactly as ompsph.hpp:132-135 / sph.hpp:240. */
 int pbf_host_grid(float h, const pbf_params *params, pbf_grid_info *out);
@@ -194,6 +198,11 @@ int pbf_host_grid(float h, const pbf_params *params, pbf_grid_info *out);
  * over coarse key buckets (bucket b covers keys [b<<shift, (b+1)<<shift)).  splits has world+1 entries. */
 int pbf_host_plan_splits(const uint64_t *bucket_hist, uint32_t n_buckets, uint32_t shift, int world,
                          uint32_t *splits);
+/* Solver constants as the host side forms them: {poly6Factor, spikyKernelFactor, poly6(0.3h), r2_max, r2_min}
+ * (sph.hpp:251-253, ompsph.hpp:211-213). */
+void pbf_host_constants(float h, float out[5]);
+/* applyMotionSinXCosZ — src/sph.hpp:147-158: the moving wall of the stock benchmark scene. */
+void pbf_host_apply_motion(const pbf_params *in, uint64_t frame, pbf_params *out);
 /* 10-bit-per-axis Morton encode/decode — src/curves.h:46-88. */
 uint32_t pbf_host_morton_encode(uint32_t x, uint32_t y, uint32_t z);
 void pbf_host_morton_decode(uint32_t key, uint32_t xyz[3]);

@@ -15,38 +15,17 @@ from pathlib import Path
 
 import numpy as np
 
-HERE = Path(__file__).resolve().parent
+import sys
 
-PARTICLE = np.dtype(
-    [("id", "<u8"), ("type", "u1"), ("_pad", "u1", (3,)), ("mass", "<f4"), ("position", "<f4", (3,)),
-     ("velocity", "<f4", (3,)), ("colour", "<f4", (4,))]
-)
-assert PARTICLE.itemsize == 56
+HERE = Path(__file__).resolve().parent
+if str(HERE.parent) not in sys.path:
+    sys.path.insert(0, str(HERE.parent))
+
+# the POD types of include/pbf_cuda.h have ONE Python definition, in the product's binding
+from pbf_sph_b200.capi import PARTICLE, GridInfo, McParams, Params  # noqa: E402,F401
 
 GAUSS_SEIDEL = 1
 SKIP_DIFFUSE = 2
-
-
-class McParams(C.Structure):
-    _fields_ = [("resolution", C.c_float), ("isolevel", C.c_float), ("particle_size", C.c_float),
-                ("particle_influence", C.c_float)]
-
-
-class Params(C.Structure):
-    _fields_ = [("dt", C.c_float), ("scale", C.c_float), ("iteration", C.c_uint64),
-                ("constant_force", C.c_float * 3), ("min_bound", C.c_float * 3), ("max_bound", C.c_float * 3),
-                ("wait", C.c_int32), ("surface_enabled", C.c_int32), ("surface", McParams)]
-
-    def copy(self) -> "Params":
-        out = Params()
-        C.memmove(C.byref(out), C.byref(self), C.sizeof(Params))
-        return out
-
-
-class GridInfo(C.Structure):
-    _fields_ = [("min_extent", C.c_float * 3), ("extent", C.c_uint32 * 3), ("grid_table_n", C.c_uint32),
-                ("key_bits", C.c_uint32), ("radix_passes", C.c_uint32), ("n_particles", C.c_uint64),
-                ("sample_size", C.c_uint32 * 3), ("n_triangles", C.c_uint32)]
 
 
 class OracleIO(C.Structure):

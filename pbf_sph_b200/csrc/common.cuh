@@ -1,0 +1,260 @@
+// common.cuh — shared declarations of the sm_100a PBF backend (context, step constants, device helpers).
+//
+// Reference semantics cited as file:line are relative to UoB-HPC/pbf-sph (src/omp/ompsph.hpp is the
+// backend whose behaviour is reproduced; see DESIGN.md for the kernel-by-kernel map).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "pbf_cuda.h"
+
+namespace pbf {
+
+// ---- physics constants: src/sph_constants.h:5-16 ---------------------------------------------------
+constexpr float kVD = 0.49f;
+constexpr float kRHO = 6378.0f;
+constexpr float kRHO_RECIP = 1.f / kRHO;
+constexpr float kEPSILON = 0.00000001f;
+constexpr float kCFM_EPSILON = 600.0f;
+constexpr float kCorrDeltaQ = 0.3f;
+constexpr float kCorrK = 0.0001f;
+constexpr float kCorrN = 4.f;
+
+// ---- Morton curve, 10 bits per axis: src/curves.h:46-88 ----------------------------------------------
+// Only bits 0..9 and 24..25 of the input survive the first mask, exactly as in the reference's size_t
+// arithmetic, so 32-bit maths on the low word is equivalent (x-1 at x==0 wraps to 1023, x+1 at 1023 to 0).
+__host__ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__host__ __device__ __forceinline__ uint32_t compact10(uint32_t v) {
+  v &= 0x09249249u;
+  v = (v | (v >> 2)) & 0x030C30C3u;
+  v = (v | (v >> 4)) & 0x0300F00Fu;
+  v = (v | (v >> 8)) & 0x030000FFu;
+  v = (v | (v >> 16)) & 0x000003FFu;
+  return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+  return spread10(x) | (spread10(y) << 1) | (spread10(z) << 2);
+}
+
+// ---- per-step constants handed to every kernel by value ------------------------------------------------
+struct StepConst {
+  float h, h2;              // smoothing length (solver ctor arg), h*h
+  float scale, dt, inv_dt;  // SphParams::scale, dt, 1/dt
+  float force[3];           // SphParams::constantForce
+  float min_bound[3], max_bound[3];
+  float min_extent[3];      // ompsph.hpp:133
+  uint32_t extent[3];       // ompsph.hpp:135
+  uint32_t G;               // sph.hpp:240
+  uint32_t n;               // particles
+  float P6, SP, P6dq;       // sph.hpp:251-253, ompsph.hpp:211-213
+  float r2_max;             // largest float r2 with sqrtf(r2) <= h  (same neighbour set as "r <= h")
+  float r2_min;             // smallest float r2 with sqrtf(r2) >= EPSILON
+  float diffuse_mix;        // dt / 750  (ompsph.hpp:203)
+  // fast-math folded factors
+  float sp_rho;             // SP * RHO_RECIP
+  float p6_over_dq;         // P6 / P6dq
+  float inv_rho;            // 1 / RHO
+};
+
+struct McConst {
+  float resolution, isolevel, particle_size, particle_influence;
+  float step;       // h / resolution
+  float threshold;  // h * scale
+  uint32_t sample[3];
+  uint32_t march[3];
+  uint64_t lattice_n, march_n;
+};
+
+// ---- strict single-precision helpers: never contracted into FMA, IEEE division / sqrt ------------------
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+// glm::min / glm::max semantics (oracle/ref/glm_shim, glm 0.9.9.8 func_common): min(a,b) = (b<a)?b:a
+__device__ __forceinline__ float glm_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float glm_max(float a, float b) { return (a < b) ? b : a; }
+
+// float -> size_t as the reference's host code performs it (truncate, two's complement for negatives)
+__device__ __forceinline__ uint32_t cell_coord(float v) { return (uint32_t)(unsigned long long)__float2ll_rz(v); }
+
+// Predicted velocity / position and Morton key of one particle: ompsph.hpp:140-153, sph.hpp:198-201.
+// Strict arithmetic: the key must be bit-exact.
+__device__ __forceinline__ void predict(const StepConst &c, const float4 pos_mass, const float4 vel, float v_out[3],
+                                        float ps_out[3], uint32_t &key) {
+  const float p[3] = {pos_mass.x, pos_mass.y, pos_mass.z};
+  const float v[3] = {vel.x, vel.y, vel.z};
+  uint32_t cc[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float f = fmul(pos_mass.w, c.force[a]);
+    v_out[a] = fadd(fmul(f, c.dt), v[a]);
+    ps_out[a] = fadd(fmul(v_out[a], c.dt), fdiv(p[a], c.scale));
+    cc[a] = cell_coord(fdiv(fsub(ps_out[a], c.min_extent[a]), c.h));
+  }
+  key = morton3(cc[0], cc[1], cc[2]);
+}
+
+// 128-bit read-only loads/stores
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+// ---- device buffer with geometric growth ------------------------------------------------------------
+template <typename T> struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n, bool keep = false, cudaStream_t s = 0) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = n + n / 8 + 256;
+    T *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) {
+      e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return e;
+      cudaStreamSynchronize(s);
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace pbf
+
+// ---- the context -----------------------------------------------------------------------------------
+struct pbf_ctx {
+  int device = 0;
+  float h = 0.1f;
+  uint32_t flags = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 148;
+
+  uint64_t n = 0;  // resident particles
+  bool have_state = false;
+  // resident SoA state; `cur` = index of the set holding the live (Z-sorted after a step) particles
+  pbf::DevBuf<float4> pos[2], vel[2], col[2];
+  pbf::DevBuf<unsigned long long> ids[2];
+  int cur = 0;      // pos/vel/ids live set
+  int cur_col = 0;  // colour live set
+  pbf::DevBuf<float4> pstar[2];
+  pbf::DevBuf<uint32_t> key_in, key_a, key_b, idx_a, idx_b;
+  uint32_t *keys_sorted = nullptr, *perm = nullptr;  // point into the ping-pong buffers after the sort
+  pbf::DevBuf<uint32_t> sort_hist, sort_tmp;
+  pbf::DevBuf<uint32_t> table;
+  pbf::DevBuf<uint32_t> scan_tmp;
+  pbf::DevBuf<uint32_t> cand_count, nbr_count;
+  pbf::DevBuf<float> rho;
+  pbf::DevBuf<pbf_particle> aos;  // staging for the drop-in path
+  pbf_particle *host_pinned = nullptr;
+  size_t host_pinned_cap = 0;
+  // marching cubes
+  pbf::DevBuf<float4> mc_pn, mc_c;
+  pbf::DevBuf<uint32_t> mc_count, mc_offset;
+  pbf::DevBuf<float> mesh_vs, mesh_ns, mesh_cs;
+  uint32_t *mc_total_dev = nullptr;   // device word: total triangles
+  uint32_t *mc_total_host = nullptr;  // pinned
+  uint64_t n_triangles = 0;
+  int *flag_dev = nullptr, *flag_host = nullptr;  // "saw a non-Fluid particle" (device word + pinned mirror)
+  // tiled neighbour kernels: list of occupied 4x4x4 cell blocks and their particle ranges
+  pbf::DevBuf<uint32_t> blk_list, blk_info;
+
+  pbf_grid_info grid{};
+  pbf::StepConst sc{};
+  pbf::McConst mc{};
+  bool mc_valid = false;
+
+  // profiling (PBF_FLAG_PROFILE)
+  static constexpr int kMaxEv = 16384;
+  cudaEvent_t ev[kMaxEv];
+  int ev_phase[kMaxEv];
+  uint64_t ev_launch0[kMaxEv];
+  int ev_used = 0;
+  bool ev_created = false;
+  pbf_profile prof{};
+};
+
+namespace pbf {
+
+// error plumbing --------------------------------------------------------------------------------------
+int fail(pbf_ctx *ctx, int code, const char *what, const char *detail);
+#define PBF_CUDA(ctx, call)                                                                \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) return pbf::fail((ctx), PBF_ERR_CUDA, #call, cudaGetErrorString(_e)); \
+  } while (0)
+#define PBF_TRY(expr)          \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != PBF_OK) return _rc; \
+  } while (0)
+
+// host-side maths shared with the oracle's definitions --------------------------------------------------
+void host_grid(float h, const pbf_params &p, pbf_grid_info &g);
+void host_step_const(float h, const pbf_params &p, const pbf_grid_info &g, uint32_t n, StepConst &sc);
+
+// phase profiling ---------------------------------------------------------------------------------------
+struct PhaseScope {
+  pbf_ctx *ctx;
+  int phase;
+  int slot;
+  PhaseScope(pbf_ctx *c, int phase);
+  ~PhaseScope();
+};
+
+// kernel launchers (each returns PBF_OK or a negative status) ----------------------------------------------
+int launch_unpack_aos(pbf_ctx *ctx, const pbf_particle *aos, uint64_t n, float4 *pos, float4 *vel, float4 *col,
+                      unsigned long long *ids, int *bad_type_flag);
+int launch_pack_aos(pbf_ctx *ctx, pbf_particle *aos, uint64_t n, const float4 *pos, const float4 *vel, const float4 *col,
+                    const unsigned long long *ids);
+int launch_predict_key(pbf_ctx *ctx, const float4 *pos, const float4 *vel, uint32_t *keys);
+// Stable LSD radix sort of (key, index) pairs over all 30 key bits; on return ctx->keys_sorted / ctx->perm are set.
+int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n);
+int launch_reorder(pbf_ctx *ctx, const uint32_t *perm, const float4 *pos_in, const float4 *vel_in, const float4 *col_in,
+                   const unsigned long long *ids_in, float4 *pos_out, float4 *vel_out, float4 *col_out,
+                   unsigned long long *ids_out, float4 *pstar_out);
+int launch_cell_table(pbf_ctx *ctx, const uint32_t *keys_sorted, uint32_t *table);
+int launch_neighbour_counts(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *pstar,
+                            uint32_t *cand, uint32_t *nbr);
+int launch_diffuse(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *col_in, float4 *col_out);
+int launch_lambda(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *pos_mass,
+                  const float4 *pstar_in, float4 *pstar_lambda_out, float *rho_out);
+int launch_delta(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *pstar_lambda_in,
+                 float4 *pstar_out);
+// global-memory neighbour kernels over the sorted range [first, first+count)
+int launch_lambda_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
+                         const uint32_t *table, const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out,
+                         float *rho_out);
+int launch_delta_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
+                        const uint32_t *table, const float4 *pstar_in, float4 *pstar_out);
+int launch_finalise(pbf_ctx *ctx, const float4 *pstar, float4 *pos, float4 *vel);
+int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *total_out_dev);
+int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col);
+
+inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+#define PBF_LAUNCH_CHECK(ctx)                                                                               \
+  do {                                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                                    \
+    if (_e != cudaSuccess) return pbf::fail((ctx), PBF_ERR_CUDA, "kernel launch", cudaGetErrorString(_e)); \
+    (ctx)->launches++;                                                                                      \
+  } while (0)
+
+}  // namespace pbf

@@ -1,0 +1,241 @@
+// sort_scan.cu — device-wide exclusive scan and the stable LSD radix sort of (Morton key, index) pairs.
+//
+// Replaces the reference's host-side std::sort of 96-byte AoS records by zIndex (ompsph.hpp:158; unstable
+// there, stable here, which is what the parity oracle defines — SURVEY.md F3).  Keys are 30-bit Morton
+// codes (curves.h:72-88); a particle predicted outside the padded grid can carry a key >= G, and the
+// reference sorts on the full key, so all 30 bits are sorted: three passes of 10-bit digits, regardless of G.
+//
+// Per pass:   digit histogram per 4096-key tile  ->  exclusive scan of the [digit][tile] matrix  ->
+//             stable scatter.  Ranks inside a tile come from __match_any_sync warp multisplit plus per-warp
+//             digit counters in shared memory, so equal digits keep their input order (stability) without
+//             atomics on the ordering path.
+#include "common.cuh"
+
+namespace pbf {
+
+namespace {
+
+// ======================================= exclusive scan =======================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+    if (lane >= (unsigned)d) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread across a 256-thread block; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total) {
+  __shared__ uint32_t warp_sums[kScanThreads / 32];
+  __shared__ uint32_t block_total;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t incl = warp_incl_scan(v);
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t s = lane < kScanThreads / 32 ? warp_sums[lane] : 0u;
+    const uint32_t si = warp_incl_scan(s);
+    if (lane < kScanThreads / 32) warp_sums[lane] = si - s;
+    if (lane == kScanThreads / 32 - 1) block_total = si;
+  }
+  __syncthreads();
+  *total = block_total;
+  return warp_sums[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t *__restrict__ in, uint64_t n,
+                                                                      uint32_t *__restrict__ sums) {
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t i = base + (uint64_t)k * kScanThreads + threadIdx.x;
+    if (i < n) s += __ldg(in + i);
+  }
+  uint32_t total;
+  block_excl_scan(s, &total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// one tile: thread t owns items [t*16, t*16+16) so the scan order is the memory order
+// `out` may alias `in` (every thread reads its items before the block-wide barrier and writes them after it)
+__global__ void __launch_bounds__(kScanThreads) scan_tile_apply_kernel(const uint32_t *in, uint64_t n,
+                                                                       const uint32_t *tile_offsets, uint32_t *out,
+                                                                       uint32_t *total_out) {
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    s += v[k];
+  }
+  uint32_t total;
+  uint32_t run = block_excl_scan(s, &total) + (tile_offsets ? tile_offsets[blockIdx.x] : 0u);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
+}
+
+// ======================================= radix sort ============================================================
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per block
+constexpr int kDigitBits = 10;
+constexpr int kBins = 1 << kDigitBits;  // 1024
+constexpr int kPasses = 3;              // 30 bits
+
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n,
+                                                                 int shift, uint32_t n_tiles,
+                                                                 uint32_t *__restrict__ tile_hist) {
+  __shared__ uint32_t hist[kBins];
+  for (int b = threadIdx.x; b < kBins; b += kSortThreads) hist[b] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const uint32_t i = base + k * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&hist[(__ldg(keys + i) >> shift) & (kBins - 1)], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < kBins; b += kSortThreads) tile_hist[(uint32_t)b * n_tiles + blockIdx.x] = hist[b];
+}
+
+template <bool kIotaValues>
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t *__restrict__ keys_in,
+                                                                    const uint32_t *__restrict__ vals_in, uint32_t n,
+                                                                    int shift, uint32_t n_tiles,
+                                                                    const uint32_t *__restrict__ tile_offsets,
+                                                                    uint32_t *__restrict__ keys_out,
+                                                                    uint32_t *__restrict__ vals_out) {
+  __shared__ uint32_t wc[kSortWarps][kBins];  // per-warp digit counters, then per-warp global bases (32 KB)
+  for (int b = threadIdx.x; b < kSortWarps * kBins; b += kSortThreads) (&wc[0][0])[b] = 0;
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint32_t warp_base = blockIdx.x * kSortTile + warp * (32 * kSortItems);
+  uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+
+  // warp w owns the contiguous range [warp_base, warp_base + 512); item k of lane l is element k*32 + l,
+  // so (k, lane) lexicographic order == memory order == the order stability must preserve
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const uint32_t i = warp_base + k * 32 + lane;
+    const bool valid = i < n;
+    key[k] = valid ? __ldg(keys_in + i) : 0u;
+    val[k] = kIotaValues ? i : (valid ? __ldg(vals_in + i) : 0u);
+    const uint32_t d = valid ? ((key[k] >> shift) & (kBins - 1)) : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+    const unsigned below = __popc(peers & lt_mask);
+    uint32_t prev = 0;
+    if (valid) prev = wc[warp][d];
+    __syncwarp();
+    if (valid && below == 0) wc[warp][d] = prev + __popc(peers);
+    __syncwarp();
+    rank[k] = prev + below;
+  }
+  __syncthreads();
+  // digit-major bases: global offset of (digit, tile) plus the counts of the lower warps
+  for (int d = threadIdx.x; d < kBins; d += kSortThreads) {
+    uint32_t run = __ldg(tile_offsets + (uint32_t)d * n_tiles + blockIdx.x);
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = wc[w][d];
+      wc[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const uint32_t i = warp_base + k * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (key[k] >> shift) & (kBins - 1);
+      const uint32_t dst = wc[warp][d] + rank[k];
+      keys_out[dst] = key[k];
+      vals_out[dst] = val[k];
+    }
+  }
+}
+
+}  // namespace
+
+// Exclusive prefix sum of n u32 values (n up to 4096^3).  `out` may alias `in`.  If total_out_dev is non-null the
+// grand total is written there (device memory).
+int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *total_out_dev) {
+  if (n == 0) {
+    if (total_out_dev) PBF_CUDA(ctx, cudaMemsetAsync(total_out_dev, 0, sizeof(uint32_t), ctx->stream));
+    return PBF_OK;
+  }
+  const uint64_t t1 = (n + kScanTile - 1) / kScanTile;
+  if (t1 == 1) {
+    scan_tile_apply_kernel<<<1, kScanThreads, 0, ctx->stream>>>(in, n, nullptr, out, total_out_dev);
+    PBF_LAUNCH_CHECK(ctx);
+    return PBF_OK;
+  }
+  const uint64_t t2 = (t1 + kScanTile - 1) / kScanTile;
+  const uint64_t t3 = (t2 + kScanTile - 1) / kScanTile;
+  if (t3 > 1) return fail(ctx, PBF_ERR_INVALID, "exclusive_scan_u32", "input too large");
+  PBF_CUDA(ctx, ctx->scan_tmp.reserve(t1 + t2 + 8));
+  uint32_t *s1 = ctx->scan_tmp.p, *s2 = ctx->scan_tmp.p + t1;
+  scan_tile_sums_kernel<<<(unsigned)t1, kScanThreads, 0, ctx->stream>>>(in, n, s1);
+  PBF_LAUNCH_CHECK(ctx);
+  if (t2 == 1) {
+    scan_tile_apply_kernel<<<1, kScanThreads, 0, ctx->stream>>>(s1, t1, nullptr, s1, nullptr);
+    PBF_LAUNCH_CHECK(ctx);
+  } else {
+    scan_tile_sums_kernel<<<(unsigned)t2, kScanThreads, 0, ctx->stream>>>(s1, t1, s2);
+    PBF_LAUNCH_CHECK(ctx);
+    scan_tile_apply_kernel<<<1, kScanThreads, 0, ctx->stream>>>(s2, t2, nullptr, s2, nullptr);
+    PBF_LAUNCH_CHECK(ctx);
+    scan_tile_apply_kernel<<<(unsigned)t2, kScanThreads, 0, ctx->stream>>>(s1, t1, s2, s1, nullptr);
+    PBF_LAUNCH_CHECK(ctx);
+  }
+  scan_tile_apply_kernel<<<(unsigned)t1, kScanThreads, 0, ctx->stream>>>(in, n, s1, out, total_out_dev);
+  PBF_LAUNCH_CHECK(ctx);
+  return PBF_OK;
+}
+
+int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n) {
+  PhaseScope ps(ctx, PBF_PH_SORT);
+  const uint32_t n_tiles = div_up(n, kSortTile);
+  PBF_CUDA(ctx, ctx->key_a.reserve(n));
+  PBF_CUDA(ctx, ctx->key_b.reserve(n));
+  PBF_CUDA(ctx, ctx->idx_a.reserve(n));
+  PBF_CUDA(ctx, ctx->idx_b.reserve(n));
+  PBF_CUDA(ctx, ctx->sort_hist.reserve((size_t)kBins * n_tiles));
+  const uint32_t *src_k = keys_in, *src_v = nullptr;
+  uint32_t *dst_k = ctx->key_a.p, *dst_v = ctx->idx_a.p;
+  for (int pass = 0; pass < kPasses; ++pass) {
+    const int shift = pass * kDigitBits;
+    sort_hist_kernel<<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, n, shift, n_tiles, ctx->sort_hist.p);
+    PBF_LAUNCH_CHECK(ctx);
+    PBF_TRY(exclusive_scan_u32(ctx, ctx->sort_hist.p, ctx->sort_hist.p, (uint64_t)kBins * n_tiles, nullptr));
+    if (pass == 0)
+      sort_scatter_kernel<true><<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, nullptr, n, shift, n_tiles,
+                                                                           ctx->sort_hist.p, dst_k, dst_v);
+    else
+      sort_scatter_kernel<false><<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, src_v, n, shift, n_tiles,
+                                                                            ctx->sort_hist.p, dst_k, dst_v);
+    PBF_LAUNCH_CHECK(ctx);
+    src_k = dst_k;
+    src_v = dst_v;
+    if (dst_k == ctx->key_a.p) { dst_k = ctx->key_b.p; dst_v = ctx->idx_b.p; } else { dst_k = ctx->key_a.p; dst_v = ctx->idx_a.p; }
+  }
+  ctx->keys_sorted = const_cast<uint32_t *>(src_k);
+  ctx->perm = const_cast<uint32_t *>(src_v);
+  return PBF_OK;
+}
+
+}  // namespace pbf

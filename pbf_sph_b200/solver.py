@@ -1,0 +1,129 @@
+"""Host-side mirror of the reference's solver interface (src/sph.hpp:119-125) over the C ABI.
+
+``Solver(h, device).advance(params, xs)`` is ``sph::Solver::advance``: one PBF step on a host particle array, which
+comes back in Z-sorted order with the optional marching-cubes mesh.  ``upload/step/download`` is the resident path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+from .capi import PARTICLE, GridInfo, Params, Profile, check, lib
+
+
+@dataclass
+class Result:  # sph::Result — sph.hpp:114-117 (queries are out of scope: drivers pass an empty Scene)
+    vs: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
+    ns: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
+    cs: np.ndarray = field(default_factory=lambda: np.zeros((0, 4), np.float32))
+
+
+class Solver:
+    def __init__(self, h: float = 0.1, device: int = 0, flags: int = 0):
+        self._L = lib()
+        self._ctx = C.c_void_p()
+        check(self._L.pbf_create(C.byref(self._ctx), C.c_float(h), device))
+        self.h = h
+        if flags:
+            self.set_flags(flags)
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._L.pbf_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc: int) -> None:
+        check(rc, self._ctx)
+
+    def set_flags(self, flags: int) -> None:
+        self._ck(self._L.pbf_set_flags(self._ctx, flags))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._ck(self._L.pbf_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    # ---- drop-in: sph::Solver::advance ---------------------------------------------------------------------
+    def advance(self, params: Params, xs: np.ndarray, mesh: bool = True) -> Result:
+        assert xs.dtype == PARTICLE and xs.flags.c_contiguous
+        nv = C.c_uint64(0)
+        self._ck(self._L.pbf_advance_host(self._ctx, C.byref(params), xs.ctypes.data, len(xs), C.byref(nv)))
+        return self.mesh() if (mesh and nv.value) else Result()
+
+    def advance_ptr(self, params: Params, ptr: int, n: int) -> int:
+        """advance() on a raw host pointer (e.g. pinned memory); returns the mesh vertex count."""
+        nv = C.c_uint64(0)
+        self._ck(self._L.pbf_advance_host(self._ctx, C.byref(params), C.c_void_p(ptr), n, C.byref(nv)))
+        return nv.value
+
+    def mesh(self) -> Result:
+        n = self.grid().n_triangles * 3
+        r = Result(np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 4), np.float32))
+        if n:
+            self._ck(self._L.pbf_mesh_download(self._ctx, r.vs.ctypes.data, r.ns.ctypes.data, r.cs.ctypes.data, n))
+        return r
+
+    # ---- resident path ------------------------------------------------------------------------------------------
+    def upload(self, xs: np.ndarray) -> None:
+        assert xs.dtype == PARTICLE and xs.flags.c_contiguous
+        self._ck(self._L.pbf_upload(self._ctx, xs.ctypes.data, len(xs)))
+
+    def step(self, params: Params) -> None:
+        self._ck(self._L.pbf_step(self._ctx, C.byref(params)))
+
+    def sync(self) -> None:
+        self._ck(self._L.pbf_sync(self._ctx))
+
+    def count(self) -> int:
+        n = C.c_uint64(0)
+        self._ck(self._L.pbf_particle_count(self._ctx, C.byref(n)))
+        return n.value
+
+    def download(self) -> np.ndarray:
+        xs = np.zeros(self.count(), PARTICLE)
+        n = C.c_uint64(0)
+        self._ck(self._L.pbf_download(self._ctx, xs.ctypes.data, len(xs), C.byref(n)))
+        return xs
+
+    # ---- introspection ------------------------------------------------------------------------------------------
+    def grid(self) -> GridInfo:
+        g = GridInfo()
+        self._ck(self._L.pbf_grid(self._ctx, C.byref(g)))
+        return g
+
+    _TAP_DTYPE = {capi.TAP_LAMBDA: np.float32, capi.TAP_RHO: np.float32, capi.TAP_IDS: np.uint64,
+                  capi.TAP_MC_FIELD: np.float32, capi.TAP_MC_COLOUR: np.float32}
+
+    def tap(self, tap: int) -> np.ndarray:
+        g = self.grid()
+        n = int(g.n_particles)
+        if tap == capi.TAP_CELL_TABLE:
+            shape = (g.grid_table_n,)
+        elif tap in (capi.TAP_MC_FIELD, capi.TAP_MC_COLOUR):
+            shape = (int(g.sample_size[0]) * int(g.sample_size[1]) * int(g.sample_size[2]), 4)
+        else:
+            shape = (n,)
+        out = np.zeros(shape, self._TAP_DTYPE.get(tap, np.uint32))
+        self._ck(self._L.pbf_debug_read(self._ctx, tap, out.ctypes.data, out.nbytes))
+        return out
+
+    def profile_reset(self) -> None:
+        self._ck(self._L.pbf_profile_reset(self._ctx))
+
+    def profile(self) -> dict:
+        p = Profile()
+        self._ck(self._L.pbf_profile_read(self._ctx, C.byref(p)))
+        return {"steps": p.steps, "ms": {name: p.ms[i] for i, name in enumerate(capi.PHASES)},
+                "launches": {name: p.launches[i] for i, name in enumerate(capi.PHASES)}}
+
+    def launch_count(self) -> int:
+        return self._L.pbf_launch_count(self._ctx)
