@@ -523,3 +523,12 @@ void pbf_oracle_constants(float h, float out[3]) {
   out[1] = spiky_factor(h);
   out[2] = poly6(CorrDeltaQ * h, out[0], h);
 }
+
+#ifdef _OPENMP
+#include <omp.h>
+void pbf_oracle_set_threads(int n) { omp_set_num_threads(n); }
+int pbf_oracle_max_threads(void) { return omp_get_max_threads(); }
+#else
+void pbf_oracle_set_threads(int n) { (void)n; }
+int pbf_oracle_max_threads(void) { return 1; }
+#endif
