@@ -192,7 +192,7 @@ def run_single(args):
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     stream = torch.cuda.Stream()
-    s = Solver(scenes.H, dev, FLAG_PROFILE)
+    s = Solver(scenes.H, dev, FLAG_PROFILE | args.flags)
     s.set_stream(stream.cuda_stream)
     s.upload(xs)
     # settle the fluid first (throughput depends on the state: ~266 candidates/particle on the initial lattice,
@@ -242,8 +242,8 @@ def run_single(args):
     ptr = L.pbf_host_alloc(nbytes)
     host = np.frombuffer((__import__("ctypes").c_char * nbytes).from_address(ptr), dtype=PARTICLE)
     host[:] = snap
-    e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(3):
+    e2e_steps = max(3, min(args.steps, 20)) if not args.no_e2e else 1
+    for _ in range(3 if not args.no_e2e else 0):
         s.advance_ptr(p, ptr, n)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -312,6 +312,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="extra PBF_FLAG_* bits (1 strict fp, 8 global-memory neighbours)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

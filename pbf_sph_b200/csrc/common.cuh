@@ -173,8 +173,11 @@ struct pbf_ctx {
   uint32_t *mc_total_host = nullptr;  // pinned
   uint64_t n_triangles = 0;
   int *flag_dev = nullptr, *flag_host = nullptr;  // "saw a non-Fluid particle" (device word + pinned mirror)
-  // tiled neighbour kernels: list of occupied 4x4x4 cell blocks and their particle ranges
-  pbf::DevBuf<uint32_t> blk_list, blk_info;
+  // tiled diffusion: queue of occupied 4x4x4 cell blocks
+  pbf::DevBuf<uint32_t> blk_list, blk_info;  // blk_info[0] = number of occupied blocks, [1] = work counter
+  // per-iteration neighbour list: nl[k * nl_stride + particle] = k-th in-radius candidate, nl_count[particle] = hits
+  pbf::DevBuf<uint32_t> nl, nl_count;
+  uint32_t nl_stride = 0;
 
   pbf_grid_info grid{};
   pbf::StepConst sc{};
@@ -244,6 +247,15 @@ int launch_lambda_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uin
                          float *rho_out);
 int launch_delta_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
                         const uint32_t *table, const float4 *pstar_in, float4 *pstar_out);
+// neighbour-list kernels (neighbour_list.cu): the production lambda/delta passes
+constexpr uint32_t kListMax = 64;  // hits stored per particle; beyond that the particle takes the one-pass path
+int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
+                       const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out);
+int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
+                      const float4 *pstar_in, float4 *pstar_out);
+// shared-memory tiled colour diffusion (diffuse_tiled.cu)
+int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *col_in,
+                         float4 *col_out);
 int launch_finalise(pbf_ctx *ctx, const float4 *pstar, float4 *pos, float4 *vel);
 int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *total_out_dev);
 int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col);

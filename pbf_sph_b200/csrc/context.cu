@@ -123,11 +123,16 @@ static void profile_collect(pbf_ctx *ctx) {
 // ---- the step ------------------------------------------------------------------------------------------------------
 static int lambda_pass(pbf_ctx *ctx, const float4 *pstar_in, float4 *pstar_out, float *rho_out) {
   PhaseScope ps(ctx, PBF_PH_LAMBDA);
+  if (!(ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS))
+    return launch_lambda_list(ctx, 0, ctx->sc.n, ctx->keys_sorted, ctx->table.p, ctx->pos[ctx->cur].p, pstar_in,
+                              pstar_out, rho_out);
   return launch_lambda_global(ctx, 0, ctx->sc.n, ctx->keys_sorted, ctx->table.p, ctx->pos[ctx->cur].p, pstar_in,
                               pstar_out, rho_out);
 }
 static int delta_pass(pbf_ctx *ctx, const float4 *pstar_in, float4 *pstar_out) {
   PhaseScope ps(ctx, PBF_PH_DELTA);
+  if (!(ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS))
+    return launch_delta_list(ctx, 0, ctx->sc.n, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out);
   return launch_delta_global(ctx, 0, ctx->sc.n, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out);
 }
 
@@ -170,6 +175,7 @@ static int step_device(pbf_ctx *ctx, const pbf_params &p) {
   ctx->cur = o;
   ctx->cur_col = oc;
   PBF_TRY(launch_cell_table(ctx, ctx->keys_sorted, ctx->table.p));
+  const bool tiled = !(ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS);
   if (ctx->flags & PBF_FLAG_DEBUG_COUNTS) {
     PBF_CUDA(ctx, ctx->cand_count.reserve(n));
     PBF_CUDA(ctx, ctx->nbr_count.reserve(n));
@@ -177,7 +183,10 @@ static int step_device(pbf_ctx *ctx, const pbf_params &p) {
                                     ctx->nbr_count.p));
   }
   PBF_CUDA(ctx, ctx->col[ctx->cur_col ^ 1].reserve(n));
-  PBF_TRY(launch_diffuse(ctx, ctx->keys_sorted, ctx->table.p, ctx->col[ctx->cur_col].p, ctx->col[ctx->cur_col ^ 1].p));
+  if (tiled)
+    PBF_TRY(launch_diffuse_tiled(ctx, ctx->keys_sorted, ctx->table.p, ctx->col[ctx->cur_col].p, ctx->col[ctx->cur_col ^ 1].p));
+  else
+    PBF_TRY(launch_diffuse(ctx, ctx->keys_sorted, ctx->table.p, ctx->col[ctx->cur_col].p, ctx->col[ctx->cur_col ^ 1].p));
   ctx->cur_col ^= 1;
   for (uint64_t it = 0; it < p.iteration; ++it) {
     PBF_TRY(lambda_pass(ctx, ctx->pstar[0].p, ctx->pstar[1].p, it + 1 == p.iteration ? ctx->rho.p : nullptr));
@@ -278,7 +287,7 @@ void pbf_destroy(pbf_ctx *ctx) {
   ctx->cand_count.release(); ctx->nbr_count.release(); ctx->rho.release(); ctx->aos.release();
   ctx->mc_pn.release(); ctx->mc_c.release(); ctx->mc_count.release(); ctx->mc_offset.release();
   ctx->mesh_vs.release(); ctx->mesh_ns.release(); ctx->mesh_cs.release();
-  ctx->blk_list.release(); ctx->blk_info.release();
+  ctx->blk_list.release(); ctx->blk_info.release(); ctx->nl.release(); ctx->nl_count.release();
   if (ctx->flag_dev) cudaFree(ctx->flag_dev);
   if (ctx->flag_host) cudaFreeHost(ctx->flag_host);
   if (ctx->mc_total_dev) cudaFree(ctx->mc_total_dev);

@@ -1,14 +1,14 @@
-// neighbour.cu — the 27-cell neighbour passes, global-memory form (one thread per particle, reads through L1/L2):
+// neighbour.cu — the 27-cell neighbour passes in their simplest form (one thread per particle, every candidate
+// evaluated in place, reads through L1/L2):
 //   neighbour_counts   parity tap: candidates / in-radius count per particle
 //   diffuse            colour averaging                         (ompsph.hpp:189-206, OCL oclsph_kernel.h:67-93)
 //   lambda             density + constraint lambda               (ompsph.hpp:217-232)
 //   delta              position correction + clamp to the box    (ompsph.hpp:235-248), Jacobi (second buffer)
 //
-// This form visits cells and particles in exactly the reference's order (sph.hpp:215-236: x fastest, then y,
-// then z; ascending sorted index inside a cell).  With PBF_FLAG_STRICT_FP every float operation is the oracle's
-// operation (no FMA contraction, IEEE div/sqrt).  The tiled shared-memory form in neighbour_tiled.cu is the
-// fast path; this one is kept as the simple cross-check (PBF_FLAG_GLOBAL_NEIGHBOURS) and for particles whose
-// key lies outside the grid.
+// Cells and particles are visited in exactly the reference's order (sph.hpp:215-236: x fastest, then y, then z;
+// ascending sorted index inside a cell).  These lambda/delta kernels are the cross-check selected by
+// PBF_FLAG_GLOBAL_NEIGHBOURS; the production path is the neighbour-list form in neighbour_list.cu.
+#include "cells.cuh"
 #include "common.cuh"
 #include "pair_math.cuh"
 
@@ -17,28 +17,6 @@ namespace pbf {
 namespace {
 
 constexpr int kNbBlock = 128;
-
-// Calls f(b) for every candidate b of a particle with Morton key `key`, in the reference's order.
-template <typename F> __device__ __forceinline__ void for_each_candidate(uint32_t key, uint32_t G,
-                                                                         const uint32_t *__restrict__ table, F &&f) {
-  const uint32_t x = compact10(key), y = compact10(key >> 1), z = compact10(key >> 2);
-#pragma unroll 1
-  for (int dz = -1; dz <= 1; ++dz) {
-    const uint32_t mz = spread10(z + (uint32_t)dz) << 2;
-#pragma unroll 1
-    for (int dy = -1; dy <= 1; ++dy) {
-      const uint32_t myz = mz | (spread10(y + (uint32_t)dy) << 1);
-#pragma unroll 1
-      for (int dx = -1; dx <= 1; ++dx) {
-        const uint32_t o = myz | spread10(x + (uint32_t)dx);
-        if (o >= G) continue;                                   // sph.hpp:206
-        const uint32_t s = __ldg(table + o);
-        const uint32_t e = (o + 1 < G) ? __ldg(table + o + 1) : s;  // sph.hpp:208: cell G-1 is always empty
-        for (uint32_t b = s; b < e; ++b) f(b);
-      }
-    }
-  }
-}
 
 __global__ void __launch_bounds__(kNbBlock) neighbour_counts_kernel(StepConst c, const uint32_t *__restrict__ keys,
                                                                     const uint32_t *__restrict__ table,

@@ -14,6 +14,13 @@
 
 namespace pbf {
 
+// 1/sqrt(x) for normal x > 0 in one MUFU (no denormal pre-scaling: every caller guarantees x >= r2_min ~ 1e-16)
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float strict_distance(const float4 a, const float4 b) {
   const float dx = fsub(b.x, a.x), dy = fsub(b.y, a.y), dz = fsub(b.z, a.z);  // glm::distance = length(b - a)
   return fsqrt(fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));          // dot = (x*x + y*y) + z*z
@@ -55,6 +62,12 @@ template <> struct LambdaAcc<true> {
   }
   // strict accumulation needs the particle's mass before the loop
   __device__ __forceinline__ void set_mass(float m) { mass = m; }
+  // in-radius test on r^2: sqrt is monotone, so fsqrt(r2) <= h  <=>  r2 <= r2_max (the same neighbour set)
+  static __device__ __forceinline__ bool test(const StepConst &c, const float4 pa, const float4 pb) {
+    const float dx = fsub(pb.x, pa.x), dy = fsub(pb.y, pa.y), dz = fsub(pb.z, pa.z);
+    return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)) <= c.r2_max;
+  }
+  __device__ __forceinline__ void add_in(const StepConst &c, const float4 pa, const float4 pb) { add(c, pa, pb); }
   __device__ __forceinline__ float finish(const StepConst &c, float /*mass*/, float &rho) {
     rho = rho_unit;
     const float norm2 = fadd(fadd(fmul(gx, gx), fmul(gy, gy)), fmul(gz, gz));
@@ -75,11 +88,28 @@ template <> struct LambdaAcc<false> {
       const float t = c.h2 - r2;
       t3 += t * t * t;
       if (r2 >= c.r2_min) {
-        const float rinv = rsqrtf(r2);
+        const float rinv = rsqrt_fast(r2);
         const float hr = c.h - r2 * rinv;
         const float s = hr * hr * rinv;
         gx += dx * s; gy += dy * s; gz += dz * s;
       }
+    }
+  }
+  static __device__ __forceinline__ bool test(const StepConst &c, const float4 pa, const float4 pb) {
+    const float dx = pa.x - pb.x, dy = pa.y - pb.y, dz = pa.z - pb.z;
+    return dx * dx + dy * dy + dz * dz <= c.r2_max;
+  }
+  // pair already known to satisfy test()
+  __device__ __forceinline__ void add_in(const StepConst &c, const float4 pa, const float4 pb) {
+    const float dx = pa.x - pb.x, dy = pa.y - pb.y, dz = pa.z - pb.z;
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    const float t = c.h2 - r2;
+    t3 += t * t * t;
+    if (r2 >= c.r2_min) {
+      const float rinv = rsqrt_fast(r2);
+      const float hr = c.h - r2 * rinv;
+      const float s = hr * hr * rinv;
+      gx += dx * s; gy += dy * s; gz += dz * s;
     }
   }
   __device__ __forceinline__ float finish(const StepConst &c, float mass, float &rho) {
@@ -109,6 +139,12 @@ template <> struct DeltaAcc<true> {
       dz = fadd(dz, fmul(fmul(fsub(pa.z, pb.z), s), factor));
     }
   }
+  static __device__ __forceinline__ bool test(const StepConst &c, const float4 pa, const float4 pb) {
+    const float ex = fsub(pb.x, pa.x), ey = fsub(pb.y, pa.y), ez = fsub(pb.z, pa.z);
+    const float r2 = fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(ez, ez));
+    return r2 <= c.r2_max && r2 >= c.r2_min;
+  }
+  __device__ __forceinline__ void add_in(const StepConst &c, const float4 pa, const float4 pb) { add(c, pa, pb); }
   __device__ __forceinline__ float4 finish(const StepConst &c, const float4 pa) {
     return clamp_to_box(c, pa.x, pa.y, pa.z, dx, dy, dz);
   }
@@ -135,7 +171,26 @@ template <> struct DeltaAcc<false> {
     const float ex = pa.x - pb.x, ey = pa.y - pb.y, ez = pa.z - pb.z;
     const float r2 = ex * ex + ey * ey + ez * ez;
     if (r2 <= c.r2_max && r2 >= c.r2_min) {
-      const float rinv = rsqrtf(r2);
+      const float rinv = rsqrt_fast(r2);
+      const float hr = c.h - r2 * rinv;
+      const float t = c.h2 - r2;
+      const float q = c.p6_over_dq * (t * t * t);
+      const float q2 = q * q;
+      const float lam = (pa.w + pb.w) - kCorrK * (q2 * q2);
+      const float s = (hr * hr * rinv) * lam;
+      dx += ex * s; dy += ey * s; dz += ez * s;
+    }
+  }
+  static __device__ __forceinline__ bool test(const StepConst &c, const float4 pa, const float4 pb) {
+    const float ex = pa.x - pb.x, ey = pa.y - pb.y, ez = pa.z - pb.z;
+    const float r2 = ex * ex + ey * ey + ez * ez;
+    return r2 <= c.r2_max && r2 >= c.r2_min;
+  }
+  __device__ __forceinline__ void add_in(const StepConst &c, const float4 pa, const float4 pb) {
+    const float ex = pa.x - pb.x, ey = pa.y - pb.y, ez = pa.z - pb.z;
+    const float r2 = ex * ex + ey * ey + ez * ez;
+    if (r2 >= c.r2_min) {  // the lambda pass's hit list contains the particle itself (r = 0)
+      const float rinv = rsqrt_fast(r2);
       const float hr = c.h - r2 * rinv;
       const float t = c.h2 - r2;
       const float q = c.p6_over_dq * (t * t * t);
