@@ -1,0 +1,47 @@
+"""Marching-cubes path (SphParams::surface) on the GPU against the oracle — ompsph.hpp:277-477.
+
+Lattice field / normals / colours within float tolerance (CUDA powf vs glibc powf differ by ulps), NaN pattern identical
+(lattice points with no particle in range carry NaN normals and colours in the reference), per-cube triangle counts and
+the total exact, and the mesh — which both sides emit in ascending cube order — compared vertex by vertex."""
+import numpy as np
+import pytest
+
+from helpers import warm
+from pbf_sph_b200 import Solver, capi, scenes
+
+pytestmark = pytest.mark.gpu
+H = scenes.H
+
+
+@pytest.mark.parametrize("count,frames", [(4000, 8), (20000, 25)])
+def test_surface_extraction_matches_oracle(gpu, oracle_mod, count, frames):
+    p, xs = scenes.two_cubes(count, 3)
+    warm(oracle_mod, H, p, xs, frames, motion=scenes.apply_motion)
+    pf = scenes.apply_motion(p, frames)
+    pf.surface_enabled = 1
+    cpu, dev = xs.copy(), xs.copy()
+    t = oracle_mod.step(H, pf, cpu, taps=True)
+    with Solver(H, 0, capi.FLAG_STRICT_FP) as s:
+        res = s.advance(pf, dev)
+        field, colour = s.tap(capi.TAP_MC_FIELD), s.tap(capi.TAP_MC_COLOUR)
+        g = s.grid()
+    assert list(g.sample_size) == list(t["grid"].sample_size)
+    assert np.array_equal(np.isnan(field), np.isnan(t["mc_field"]))
+    assert np.array_equal(np.isnan(colour), np.isnan(t["mc_colour"]))
+    assert np.allclose(field[:, 0], t["mc_field"][:, 0], rtol=2e-5, atol=1e-4)
+    assert np.allclose(field[:, 1:], t["mc_field"][:, 1:], rtol=0, atol=2e-4, equal_nan=True)  # unit normals
+    assert np.allclose(colour, t["mc_colour"], rtol=1e-5, atol=1e-6, equal_nan=True)
+    # triangle counts: a lattice value within float noise of the isolevel could flip a cube; report if it does
+    assert g.n_triangles * 3 == len(res.vs)
+    assert len(res.vs) == t["n_vertices"], (len(res.vs), t["n_vertices"])
+    assert len(res.vs) > 1000, "scene must actually produce a surface"
+    assert np.allclose(res.vs, t["mesh_vs"], rtol=0, atol=2e-2, equal_nan=True)   # positions, domain = 1000
+    assert np.allclose(res.ns, t["mesh_ns"], rtol=0, atol=2e-3, equal_nan=True)
+    assert np.allclose(res.cs, t["mesh_cs"], rtol=0, atol=2e-4, equal_nan=True)
+
+
+def test_surface_off_gives_empty_mesh(gpu):
+    p, xs = scenes.two_cubes(2000, 2)
+    with Solver(H, 0) as s:
+        res = s.advance(p, xs)
+        assert len(res.vs) == 0 and s.grid().n_triangles == 0
