@@ -169,21 +169,33 @@ int pbf_profile_read(pbf_ctx *ctx, pbf_profile *out);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t pbf_launch_count(const pbf_ctx *ctx);
 
-/* ---- multi-GPU: Z-curve slab decomposition, one process (rank) per GPU ----------------------------- */
-/* The reference is single-device; this is the north-star extension (SURVEY §8e).  Rank r owns the
- * Morton key range [split[r], split[r+1]).  Ghost/migrant exchange uses ncclSend/ncclRecv. */
+/* ---- multi-GPU: Z-curve slab decomposition, one rank per GPU ----------------------------------------- */
+/* The reference is single-device; this is the north-star extension (SURVEY §8e, DESIGN.md §6).  Rank r owns the
+ * Morton key range [split[r], split[r+1]); per step: migrants to their owners, then a 2-cell ghost layer whose
+ * pStar is refreshed once per solver iteration.  Two transports:
+ *   NCCL   one process per GPU: rank 0 makes the id (pbf_dist_unique_id), the launcher distributes it
+ *          (bench.py: torch.distributed.broadcast), every rank calls pbf_dist_init; ncclSend/ncclRecv groups.
+ *   LOCAL  all ranks are contexts of ONE process (any devices, may share a device): pbf_dist_init_local;
+ *          exchanges are device-to-device copies.  pbf_dist_step on any member steps the whole group.
+ * Marching cubes is not available on the slab path (params->surface_enabled must be 0). */
 #define PBF_NCCL_ID_BYTES 128
 int pbf_dist_unique_id(uint8_t id[PBF_NCCL_ID_BYTES]);
 int pbf_dist_init(pbf_ctx *ctx, const uint8_t id[PBF_NCCL_ID_BYTES], int rank, int world);
-/* Scatter-free start: every rank passes the FULL initial particle set; each keeps what it owns. */
-int pbf_dist_upload(pbf_ctx *ctx, const pbf_params *params, const pbf_particle *xs, uint64_t n);
+int pbf_dist_init_local(pbf_ctx **ctxs, int world);
+/* This rank's share of the particles — ANY subset; the first step migrates every particle to its owner. */
+int pbf_dist_upload(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n);
+/* Collective: one PBF step of the whole fluid (asynchronous on the context's stream between exchanges). */
 int pbf_dist_step(pbf_ctx *ctx, const pbf_params *params);
-/* Owned particles of this rank, Z-sorted. */
+/* Owned particles of this rank, Z-sorted (concatenating ranks 0..world-1 gives the global Z order). */
 int pbf_dist_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_t *n_out);
+/* Re-plan the key splits from a global key histogram every `steps` steps (default 16; 0 = only at the first step). */
+int pbf_dist_set_replan(pbf_ctx *ctx, uint32_t steps);
 typedef struct pbf_dist_stats {
-  uint64_t owned, ghosts, migrants_out, migrants_in;
-  uint64_t halo_bytes_per_iteration;
-  uint32_t key_lo, key_hi;
+  uint64_t owned, ghosts, migrants_out, migrants_in; /* of the last step */
+  uint64_t halo_bytes_per_iteration;                 /* pStar bytes this rank SENDS per solver iteration */
+  uint32_t key_lo, key_hi;                           /* owned Morton range */
+  uint32_t ghost_ring1;                              /* ghosts whose lambda is computed locally */
+  uint32_t boundary;                                 /* owned particles some other rank holds as ghosts */
 } pbf_dist_stats;
 int pbf_dist_stats_read(pbf_ctx *ctx, pbf_dist_stats *out);
 

@@ -65,7 +65,7 @@ class Profile(C.Structure):
 class DistStats(C.Structure):
     _fields_ = [("owned", C.c_uint64), ("ghosts", C.c_uint64), ("migrants_out", C.c_uint64),
                 ("migrants_in", C.c_uint64), ("halo_bytes_per_iteration", C.c_uint64), ("key_lo", C.c_uint32),
-                ("key_hi", C.c_uint32)]
+                ("key_hi", C.c_uint32), ("ghost_ring1", C.c_uint32), ("boundary", C.c_uint32)]
 
 
 # every symbol include/pbf_cuda.h declares (tests/test_abi.py checks the library exports each one)
@@ -73,8 +73,8 @@ EXPORTS = [
     "pbf_create", "pbf_destroy", "pbf_last_error", "pbf_abi_version", "pbf_set_flags", "pbf_set_stream",
     "pbf_advance_host", "pbf_mesh_download", "pbf_upload", "pbf_step", "pbf_sync", "pbf_download",
     "pbf_particle_count", "pbf_device_state", "pbf_grid", "pbf_debug_read", "pbf_profile_reset", "pbf_profile_read",
-    "pbf_launch_count", "pbf_dist_unique_id", "pbf_dist_init", "pbf_dist_upload", "pbf_dist_step",
-    "pbf_dist_download", "pbf_dist_stats_read", "pbf_host_alloc", "pbf_host_free", "pbf_host_grid",
+    "pbf_launch_count", "pbf_dist_unique_id", "pbf_dist_init", "pbf_dist_init_local", "pbf_dist_upload",
+    "pbf_dist_step", "pbf_dist_download", "pbf_dist_set_replan", "pbf_dist_stats_read", "pbf_host_alloc", "pbf_host_free", "pbf_host_grid",
     "pbf_host_plan_splits", "pbf_host_constants", "pbf_host_morton_encode", "pbf_host_morton_decode",
     "pbf_host_apply_motion",
 ]
@@ -121,7 +121,9 @@ def lib() -> C.CDLL:
         "pbf_launch_count": ([vp], u64),
         "pbf_dist_unique_id": ([vp], i32),
         "pbf_dist_init": ([vp, vp, i32, i32], i32),
-        "pbf_dist_upload": ([vp, P(Params), vp, u64], i32),
+        "pbf_dist_init_local": ([P(vp), i32], i32),
+        "pbf_dist_set_replan": ([vp, u32], i32),
+        "pbf_dist_upload": ([vp, vp, u64], i32),
         "pbf_dist_step": ([vp, P(Params)], i32),
         "pbf_dist_download": ([vp, vp, u64, P(u64)], i32),
         "pbf_dist_stats_read": ([vp, P(DistStats)], i32),

@@ -184,6 +184,9 @@ struct pbf_ctx {
   pbf::McConst mc{};
   bool mc_valid = false;
 
+  // multi-GPU (dist.cu): slab state, or nullptr on a single-device context
+  struct pbf_dist_state *dist = nullptr;
+
   // profiling (PBF_FLAG_PROFILE)
   static constexpr int kMaxEv = 16384;
   cudaEvent_t ev[kMaxEv];
@@ -229,7 +232,8 @@ int launch_pack_aos(pbf_ctx *ctx, pbf_particle *aos, uint64_t n, const float4 *p
                     const unsigned long long *ids);
 int launch_predict_key(pbf_ctx *ctx, const float4 *pos, const float4 *vel, uint32_t *keys);
 // Stable LSD radix sort of (key, index) pairs over all 30 key bits; on return ctx->keys_sorted / ctx->perm are set.
-int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n);
+// vals_in == nullptr sorts (key, 0..n-1); otherwise the given values travel with the keys (multi-GPU merge, dist.cu).
+int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n, const uint32_t *vals_in = nullptr);
 int launch_reorder(pbf_ctx *ctx, const uint32_t *perm, const float4 *pos_in, const float4 *vel_in, const float4 *col_in,
                    const unsigned long long *ids_in, float4 *pos_out, float4 *vel_out, float4 *col_out,
                    unsigned long long *ids_out, float4 *pstar_out);
@@ -250,15 +254,21 @@ int launch_delta_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint
 // neighbour-list kernels (neighbour_list.cu): the production lambda/delta passes
 constexpr uint32_t kListMax = 64;  // hits stored per particle; beyond that the particle takes the one-pass path
 int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                       const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out);
+                       const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
+                       const uint32_t *subset = nullptr, uint32_t subset_base = 0);
+// subset != nullptr: thread t handles particle subset_base + subset[t] instead of first + t (multi-GPU boundary /
+// interior / ring-1 index lists, dist.cu)
 int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                      const float4 *pstar_in, float4 *pstar_out);
+                      const float4 *pstar_in, float4 *pstar_out, const uint32_t *subset = nullptr,
+                      uint32_t subset_base = 0);
 // shared-memory tiled colour diffusion (diffuse_tiled.cu)
 int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *col_in,
                          float4 *col_out);
 int launch_finalise(pbf_ctx *ctx, const float4 *pstar, float4 *pos, float4 *vel);
 int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *total_out_dev);
 int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col);
+
+void dist_release(pbf_ctx *ctx);  // dist.cu
 
 inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 

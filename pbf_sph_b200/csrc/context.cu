@@ -279,6 +279,7 @@ void pbf_destroy(pbf_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  dist_release(ctx);
   for (int i = 0; i < 2; ++i) {
     ctx->pos[i].release(); ctx->vel[i].release(); ctx->col[i].release(); ctx->ids[i].release(); ctx->pstar[i].release();
   }
@@ -323,6 +324,7 @@ int pbf_set_stream(pbf_ctx *ctx, void *cuda_stream) {
 int pbf_advance_host(pbf_ctx *ctx, const pbf_params *params, pbf_particle *xs, uint64_t n, uint64_t *n_mesh_vertices) {
   PBF_ENTER(ctx);
   if (n_mesh_vertices) *n_mesh_vertices = 0;
+  if (ctx->dist) return fail(ctx, PBF_ERR_STATE, "pbf_advance_host", "this context is a slab rank: use pbf_dist_step");
   if (n == 0) { ctx->n = 0; return PBF_OK; }  // ompsph.hpp:122-126: nothing to do
   if (!xs) return fail(ctx, PBF_ERR_INVALID, "xs", "NULL");
   PBF_TRY(validate(ctx, params));
@@ -369,6 +371,7 @@ int pbf_step(pbf_ctx *ctx, const pbf_params *params) {
   PBF_ENTER(ctx);
   if (!ctx->have_state) return fail(ctx, PBF_ERR_STATE, "pbf_step", "no resident particles: call pbf_upload first");
   if (!params) return fail(ctx, PBF_ERR_INVALID, "params", "NULL");
+  if (ctx->dist) return fail(ctx, PBF_ERR_STATE, "pbf_step", "this context is a slab rank: use pbf_dist_step");
   return step_device(ctx, *params);
 }
 
@@ -382,6 +385,7 @@ int pbf_sync(pbf_ctx *ctx) {
 int pbf_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_t *n_out) {
   PBF_ENTER(ctx);
   if (!ctx->have_state) return fail(ctx, PBF_ERR_STATE, "pbf_download", "no resident particles");
+  if (ctx->dist) return fail(ctx, PBF_ERR_STATE, "pbf_download", "this context is a slab rank: use pbf_dist_download");
   if (n_out) *n_out = ctx->n;
   if (capacity < ctx->n) return fail(ctx, PBF_ERR_CAPACITY, "pbf_download", "capacity too small");
   if (ctx->n && !xs) return fail(ctx, PBF_ERR_INVALID, "xs", "NULL");
@@ -420,7 +424,7 @@ int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes) {
   PBF_ENTER(ctx);
   if (!dst) return fail(ctx, PBF_ERR_INVALID, "dst", "NULL");
   PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const uint64_t n = ctx->n;
+  const uint64_t n = ctx->dist ? ctx->sc.n : ctx->n;  // slab path: taps cover the local array (ghosts + owned)
   const void *src = nullptr;
   uint64_t bytes = 0;
   bool strided_w = false;

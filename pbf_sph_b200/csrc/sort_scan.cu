@@ -207,22 +207,23 @@ int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t
   return PBF_OK;
 }
 
-int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n) {
+int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n, const uint32_t *vals_in) {
   PhaseScope ps(ctx, PBF_PH_SORT);
+  if (n == 0) { ctx->keys_sorted = ctx->key_a.p; ctx->perm = ctx->idx_a.p; return PBF_OK; }
   const uint32_t n_tiles = div_up(n, kSortTile);
   PBF_CUDA(ctx, ctx->key_a.reserve(n));
   PBF_CUDA(ctx, ctx->key_b.reserve(n));
   PBF_CUDA(ctx, ctx->idx_a.reserve(n));
   PBF_CUDA(ctx, ctx->idx_b.reserve(n));
   PBF_CUDA(ctx, ctx->sort_hist.reserve((size_t)kBins * n_tiles));
-  const uint32_t *src_k = keys_in, *src_v = nullptr;
+  const uint32_t *src_k = keys_in, *src_v = vals_in;  // vals_in == nullptr: values are 0..n-1
   uint32_t *dst_k = ctx->key_a.p, *dst_v = ctx->idx_a.p;
   for (int pass = 0; pass < kPasses; ++pass) {
     const int shift = pass * kDigitBits;
     sort_hist_kernel<<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, n, shift, n_tiles, ctx->sort_hist.p);
     PBF_LAUNCH_CHECK(ctx);
     PBF_TRY(exclusive_scan_u32(ctx, ctx->sort_hist.p, ctx->sort_hist.p, (uint64_t)kBins * n_tiles, nullptr));
-    if (pass == 0)
+    if (pass == 0 && !vals_in)
       sort_scatter_kernel<true><<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, nullptr, n, shift, n_tiles,
                                                                            ctx->sort_hist.p, dst_k, dst_v);
     else

@@ -1,0 +1,225 @@
+"""Multi-GPU slab path over the C ABI (include/pbf_cuda.h "multi-GPU"): one rank per GPU, Z-curve slab decomposition.
+
+* ``SlabRank``    one rank of an NCCL job (one process per GPU; torch.distributed carries the NCCL unique id).
+* ``LocalGroup``  all ranks as contexts of this process (device-to-device copies) — the 1-GPU parity tests.
+* ``shard``       the share of a particle array a rank uploads (any split works: step 1 migrates to the owners).
+* ``bench_main``  the N > 1 arm of bench.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import capi
+from .capi import PARTICLE, DistStats, Params, check, lib
+from .solver import Solver
+
+
+def shard(xs: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Contiguous block `rank` of `world` of the input array (sizes differ by at most one)."""
+    n = len(xs)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    return np.ascontiguousarray(xs[lo:hi])
+
+
+def stats_dict(s: DistStats) -> dict:
+    return {k: int(getattr(s, k)) for k, _ in DistStats._fields_}
+
+
+class _RankOps:
+    """Calls shared by both transports; `self.s` is the rank's Solver (context)."""
+
+    s: Solver
+
+    def upload(self, xs: np.ndarray) -> None:
+        assert xs.dtype == PARTICLE and xs.flags.c_contiguous
+        self.s._ck(self.s._L.pbf_dist_upload(self.s._ctx, xs.ctypes.data, len(xs)))
+
+    def download(self) -> np.ndarray:
+        xs = np.zeros(self.s.count(), PARTICLE)
+        n = C.c_uint64(0)
+        self.s._ck(self.s._L.pbf_dist_download(self.s._ctx, xs.ctypes.data, len(xs), C.byref(n)))
+        return xs[: n.value]
+
+    def stats(self) -> dict:
+        st = DistStats()
+        self.s._ck(self.s._L.pbf_dist_stats_read(self.s._ctx, C.byref(st)))
+        return stats_dict(st)
+
+    def set_replan(self, steps: int) -> None:
+        self.s._ck(self.s._L.pbf_dist_set_replan(self.s._ctx, steps))
+
+
+class SlabRank(_RankOps):
+    """One rank of the NCCL transport.  `id_bytes` = the 128-byte id from ``unique_id()`` on rank 0."""
+
+    def __init__(self, h: float, device: int, rank: int, world: int, id_bytes: bytes, flags: int = 0):
+        self.s = Solver(h, device, flags)
+        self.rank, self.world = rank, world
+        buf = (C.c_uint8 * capi.NCCL_ID_BYTES).from_buffer_copy(id_bytes)
+        self.s._ck(self.s._L.pbf_dist_init(self.s._ctx, buf, rank, world))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * capi.NCCL_ID_BYTES)()
+        check(lib().pbf_dist_unique_id(buf))
+        return bytes(buf)
+
+    def step(self, params: Params) -> None:
+        self.s._ck(self.s._L.pbf_dist_step(self.s._ctx, C.byref(params)))
+
+    def close(self) -> None:
+        self.s.close()
+
+
+class _LocalRank(_RankOps):
+    def __init__(self, s: Solver):
+        self.s = s
+
+
+class LocalGroup:
+    """`world` slab ranks inside this process (devices[i] = CUDA ordinal of rank i; they may coincide)."""
+
+    def __init__(self, h: float, devices: list[int], flags: int = 0):
+        self.solvers = [Solver(h, d, flags) for d in devices]
+        self.ranks = [_LocalRank(s) for s in self.solvers]
+        arr = (C.c_void_p * len(devices))(*[s._ctx for s in self.solvers])
+        check(lib().pbf_dist_init_local(arr, len(devices)), self.solvers[0]._ctx)
+
+    @property
+    def world(self) -> int:
+        return len(self.ranks)
+
+    def upload(self, xs: np.ndarray) -> None:
+        for r, rank in enumerate(self.ranks):
+            rank.upload(shard(xs, r, self.world))
+
+    def step(self, params: Params) -> None:
+        s = self.solvers[0]
+        s._ck(s._L.pbf_dist_step(s._ctx, C.byref(params)))
+
+    def sync(self) -> None:
+        for s in self.solvers:
+            s.sync()
+
+    def download(self) -> np.ndarray:
+        """All particles, rank 0 first: the global Z order."""
+        return np.concatenate([r.download() for r in self.ranks])
+
+    def close(self) -> None:
+        for s in self.solvers:
+            s.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+# ------------------------------------------------------------------------------------------------- bench.py, N > 1
+def bench_main(args, workload, ClockSampler, METRIC, UNIT) -> None:
+    """One rank per GPU under torchrun: weak scaling (the dam-break block grows so that every GPU holds ~1 M
+    particles), device time by CUDA events, max over ranks, rank 0 prints the JSON line."""
+    import torch
+    import torch.distributed as dist
+    from . import scenes
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name, desc, p, xs = workload(args.workload, world)
+    n_total, iters = len(xs), int(p.iteration)
+
+    idt = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(SlabRank.unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    sr = SlabRank(scenes.H, local, rank, world, bytes(idt.cpu().numpy().tobytes()), capi.FLAG_PROFILE | args.flags)
+    stream = torch.cuda.Stream()
+    sr.s.set_stream(stream.cuda_stream)
+    mine = shard(xs, rank, world)
+    del xs
+    sr.upload(mine)
+    for _ in range(args.settle + args.warmup):
+        sr.step(p)
+    sr.s.sync()
+    sr.s.profile_reset()
+    l0 = sr.s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            sr.step(p)
+        e1.record(stream)
+        torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = sr.s.launch_count() - l0
+    prof = sr.s.profile()
+    st = sr.stats()
+
+    # end to end: every step uploads the rank's particles from pinned host memory and reads them back into it
+    import time
+    L = lib()
+    n_cur = sr.s.count()
+    cap = int(n_cur * 1.5) + 4096
+    ptr = L.pbf_host_alloc(cap * PARTICLE.itemsize)
+    n_out = C.c_uint64(0)
+    sr.s._ck(L.pbf_dist_download(sr.s._ctx, C.c_void_p(ptr), cap, C.byref(n_out)))
+    e2e_steps = max(3, min(args.steps, 10))
+    moved = 0
+
+    def roundtrip(n: int) -> int:
+        sr.s._ck(L.pbf_dist_upload(sr.s._ctx, C.c_void_p(ptr), n))
+        sr.step(p)
+        sr.s._ck(L.pbf_dist_download(sr.s._ctx, C.c_void_p(ptr), cap, C.byref(n_out)))
+        return int(n_out.value)
+
+    n_cur = int(n_out.value)
+    for _ in range(2):
+        n_cur = roundtrip(n_cur)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        moved += n_cur
+        n_cur = roundtrip(n_cur)
+    torch.cuda.synchronize(); dist.barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    moved_t = torch.tensor([moved], device="cuda", dtype=torch.float64)
+    dist.all_reduce(moved_t, op=dist.ReduceOp.SUM)
+    L.pbf_host_free(ptr)
+
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {"rank": rank, **st, "launches": launches,
+                                      "ms": {k: round(v / args.steps, 4) for k, v in prof["ms"].items() if v > 0}})
+    clocks = clk.summary()
+    if rank == 0:
+        value = n_total * iters * args.steps / (ms_total * 1e-3)
+        e2e_val = n_total * iters * e2e_steps / float(e2e_s.item())
+        per_step_bytes = float(moved_t.item()) / e2e_steps * PARTICLE.itemsize
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "name": name, "particles": n_total, "solver_iterations": iters,
+                       "settle_steps": args.settle, "decomposition": "Z-curve slabs, NCCL send/recv halo per solver iteration",
+                       "l2": "no flush: the per-step working set exceeds the 126 MB L2"},
+            "particle_steps_per_sec": n_total * args.steps / (ms_total * 1e-3),
+            "roofline": None, "cpu_baseline": None,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(per_step_bytes),
+                    "d2h_bytes_per_step": int(per_step_bytes), "steps": e2e_steps,
+                    "api": "pbf_dist_upload (host AoS) -> pbf_dist_step -> pbf_dist_download, every step, all ranks"},
+            "gpu_launches": int(sum(g["launches"] for g in gathered)), "ranks": gathered, "clocks": clocks,
+        }))
+    sr.close()
+    dist.destroy_process_group()

@@ -1,0 +1,102 @@
+"""Slab-decomposed (multi-rank) step against the single-device step — include/pbf_cuda.h "multi-GPU", DESIGN.md §6.
+
+The ranks run as contexts of one process on cuda:0 (LOCAL transport: the same phases, kernels and message layout
+as the NCCL transport; only the copies differ), so this runs on a 1-GPU box.  Every rank uploads a consecutive block
+of the input array; the merged stable sort then reproduces the single-device particle order cell by cell, ghosts
+carry identical values, and every sum is formed in the same order: the result must be BIT-IDENTICAL to the
+single-device path (which tests/test_parity_gpu.py pins to the oracle), for any number of ranks."""
+import numpy as np
+import pytest
+
+from helpers import by_id
+from pbf_sph_b200 import Solver, capi, scenes
+from pbf_sph_b200.dist import LocalGroup
+
+pytestmark = pytest.mark.gpu
+H = scenes.H
+
+
+def run_single(p, xs, frames, motion):
+    out = []
+    with Solver(H, 0) as s:
+        s.upload(xs)
+        for f in range(frames):
+            s.step(scenes.apply_motion(p, f) if motion else p)
+            out.append(s.download())
+    return out
+
+
+def run_group(p, xs, frames, motion, world, replan):
+    out, stats = [], []
+    with LocalGroup(H, [0] * world) as g:
+        g.ranks[0].set_replan(replan)
+        g.upload(xs)
+        for f in range(frames):
+            g.step(scenes.apply_motion(p, f) if motion else p)
+            out.append(g.download())
+            stats.append([r.stats() for r in g.ranks])
+    return out, stats
+
+
+@pytest.mark.parametrize("world,replan", [(2, 16), (3, 2), (4, 1), (8, 3)])
+def test_slab_group_is_bit_identical_to_single_device(gpu, world, replan):
+    p, xs = scenes.two_cubes(20000, 4)
+    frames = 8
+    ref = run_single(p, xs.copy(), frames, True)
+    got, stats = run_group(p, xs.copy(), frames, True, world, replan)
+    for f in range(frames):
+        a, b = ref[f], got[f]
+        assert len(a) == len(b)
+        # concatenating the ranks gives the global Z order, i.e. exactly the single-device output order
+        assert np.array_equal(a["id"], b["id"]), f"frame {f}: particle order differs"
+        for field in ("position", "velocity", "colour", "mass"):
+            assert np.array_equal(a[field].view(np.uint32), b[field].view(np.uint32)), f"frame {f}: {field} differs"
+    last = stats[-1]
+    assert sum(s["owned"] for s in last) == len(xs)
+    # the decomposition really is distributed: every rank owns particles and ghosts flow
+    assert all(s["owned"] > 0 for s in last)
+    assert sum(s["ghosts"] for s in last) > 0
+    assert any(any(s["migrants_in"] for s in st) for st in stats)
+    # key ranges tile [0, 2^30)
+    assert last[0]["key_lo"] == 0 and last[-1]["key_hi"] == 1 << 30
+    for a, b in zip(last[:-1], last[1:]):
+        assert a["key_hi"] == b["key_lo"]
+
+
+def test_slab_group_dam_break_balance_and_parity(gpu):
+    p, xs = scenes.dam_break(40, 4)
+    frames = 6
+    ref = run_single(p, xs.copy(), frames, False)
+    got, stats = run_group(p, xs.copy(), frames, False, 4, 2)
+    a, b = ref[-1], got[-1]
+    assert np.array_equal(a["id"], b["id"])
+    assert np.array_equal(a["position"].view(np.uint32), b["position"].view(np.uint32))
+    owned = [s["owned"] for s in stats[-1]]
+    assert max(owned) < 1.25 * len(xs) / 4, owned  # histogram splits balance the particle counts
+    ring1 = sum(s["ghost_ring1"] for s in stats[-1])
+    ghosts = sum(s["ghosts"] for s in stats[-1])
+    assert 0 < ring1 < ghosts  # lambda is computed for the inner ghost ring only
+
+
+def test_slab_rank_with_uneven_and_empty_uploads(gpu):
+    """Any initial distribution is legal: here rank 0 uploads everything and rank 1 nothing."""
+    p, xs = scenes.two_cubes(4000, 3)
+    ref = run_single(p, xs.copy(), 3, False)
+    with LocalGroup(H, [0, 0]) as g:
+        g.ranks[0].upload(xs)
+        g.ranks[1].upload(xs[:0])
+        for _ in range(3):
+            g.step(p)
+        out = g.download()
+    assert np.array_equal(by_id(ref[-1])["position"].view(np.uint32), by_id(out)["position"].view(np.uint32))
+
+
+def test_slab_path_rejects_surface_and_single_device_calls(gpu):
+    p, xs = scenes.two_cubes(2000, 2)
+    with LocalGroup(H, [0, 0]) as g:
+        g.upload(xs)
+        with pytest.raises(capi.PbfError):
+            g.solvers[0].step(p)  # pbf_step on a slab rank
+        p.surface_enabled = 1
+        with pytest.raises(capi.PbfError):
+            g.step(p)
