@@ -303,7 +303,17 @@ def run_multi(args):
     dist.bench_main(args, workload, ClockSampler, METRIC, UNIT)
 
 
+def _protect_stdout():
+    """Native libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

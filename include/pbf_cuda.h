@@ -188,7 +188,7 @@ int pbf_dist_upload(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n);
 int pbf_dist_step(pbf_ctx *ctx, const pbf_params *params);
 /* Owned particles of this rank, Z-sorted (concatenating ranks 0..world-1 gives the global Z order). */
 int pbf_dist_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_t *n_out);
-/* Re-plan the key splits from a global key histogram every `steps` steps (default 16; 0 = only at the first step). */
+/* Re-plan the key splits from a global key histogram every `steps` steps (default 4; 0 = only at the first step). */
 int pbf_dist_set_replan(pbf_ctx *ctx, uint32_t steps);
 typedef struct pbf_dist_stats {
   uint64_t owned, ghosts, migrants_out, migrants_in; /* of the last step */

@@ -255,12 +255,10 @@ int launch_delta_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint
 constexpr uint32_t kListMax = 64;  // hits stored per particle; beyond that the particle takes the one-pass path
 int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                        const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
-                       const uint32_t *subset = nullptr, uint32_t subset_base = 0);
-// subset != nullptr: thread t handles particle subset_base + subset[t] instead of first + t (multi-GPU boundary /
-// interior / ring-1 index lists, dist.cu)
+                       const uint32_t *role = nullptr, uint32_t want = 0);
+// role != nullptr: particle a is processed only when role[a] & want (multi-GPU: ring-1 / boundary / interior, dist.cu)
 int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                      const float4 *pstar_in, float4 *pstar_out, const uint32_t *subset = nullptr,
-                      uint32_t subset_base = 0);
+                      const float4 *pstar_in, float4 *pstar_out, const uint32_t *role = nullptr, uint32_t want = 0);
 // shared-memory tiled colour diffusion (diffuse_tiled.cu)
 int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *col_in,
                          float4 *col_out);

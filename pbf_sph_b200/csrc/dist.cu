@@ -5,12 +5,15 @@
 // [split[r], split[r+1]).  Keys and the cell table are computed once per step and reused by every solver iteration
 // (ompsph.hpp:215-249), so ownership, the ghost-cell sets and the send lists are static within a step:
 //
-//   A  predict_key on the owned particles; (every `replan` steps) global key histogram -> new splits
-//      stable radix sort; in sorted order the particles leaving for rank d form ONE contiguous segment
+//   A  predict_key on the owned particles; (every `replan` steps) global key histogram -> new splits;
+//      classify every particle by the rank owning its key
 //   x1 all-gather of the per-destination counts
-//   B  pack the leaving segments; x2 all-to-all of the migrants (pos, vel, colour, id, key)
-//   C  merge: stable sort of [kept | received from rank 0 | rank 1 | ...]; ghost masks: a cell is sent to every rank
-//      owning a cell within Chebyshev distance 2 (delta needs lambda of ring-1 ghosts, whose lambda needs ring 2)
+//   B  stable destination-major list of the leaving particles, pack; x2 all-to-all of the migrants
+//      (pos, vel, colour, id, key)
+//   C  ONE stable radix sort of [arrivals from lower ranks | kept | arrivals from higher ranks] — the order that
+//      reproduces the single-device stable sort when the ranks' inputs are consecutive blocks of one array;
+//      ghost masks: a cell is sent to every rank owning a cell within Chebyshev distance 2 (delta needs lambda of
+//      ring-1 ghosts, whose lambda needs ring 2)
 //   x3 all-gather of the ghost counts
 //   D  reorder (gather + predict) into the local arrays [ghosts below | owned | ghosts above], which are globally
 //      key-sorted because ranks own ascending key ranges; pack the ghost payload
@@ -110,17 +113,16 @@ struct pbf_dist_state {
   cudaStream_t comm_stream = nullptr;             // halo exchange overlapped with the interior delta pass
   cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
   uint64_t step_index = 0;
-  uint32_t replan_every = 16;
+  uint32_t replan_every = 4;
   uint32_t hist_shift = 0, hist_buckets = 0;
   std::vector<uint32_t> splits;                   // world + 1 key boundaries
   uint32_t own_off = 0;                           // first owned particle in the local arrays (= ghosts below)
-  uint32_t n_in = 0, n_keep = 0, n_own = 0, n_glo = 0, n_ghi = 0, n_local = 0, n_send = 0, n_boundary = 0, n_ring1 = 0;
+  uint32_t n_in = 0, n_keep = 0, n_own = 0, n_glo = 0, n_ghi = 0, n_local = 0, n_send = 0;
   uint32_t total_in = 0, total_out = 0, in_lo = 0;
   bool any_migrants = false, any_ghosts = false, any_outside = false;
-  std::vector<uint32_t> bounds;                   // host copy of d_bounds
   // device scratch
-  DevBuf<uint32_t> d_splits, d_bounds, d_row, d_all, d_hist;
-  DevBuf<uint32_t> mask, send_idx, blk_cnt, k2, v2, keys_local, sub_boundary, sub_interior, sub_lambda, sub_cnt;
+  DevBuf<uint32_t> d_splits, d_row, d_all, d_hist;
+  DevBuf<uint32_t> mask, send_idx, blk_cnt, k2, v2, keys_local, role, sub_cnt;
   DevBuf<float4> sb_a, sb_b, sb_c;
   DevBuf<unsigned long long> sb_id;
   DevBuf<uint32_t> sb_key;
@@ -128,9 +130,9 @@ struct pbf_dist_state {
   std::vector<Msg> msgs;
   pbf_dist_stats stats{};
   void release() {
-    d_splits.release(); d_bounds.release(); d_row.release(); d_all.release(); d_hist.release();
+    d_splits.release(); d_row.release(); d_all.release(); d_hist.release();
     mask.release(); send_idx.release(); blk_cnt.release(); k2.release(); v2.release(); keys_local.release();
-    sub_boundary.release(); sub_interior.release(); sub_lambda.release(); sub_cnt.release();
+    role.release(); sub_cnt.release();
     sb_a.release(); sb_b.release(); sb_c.release(); sb_id.release(); sb_key.release();
     if (h_pinned) cudaFreeHost(h_pinned);
     if (comm_stream) cudaStreamDestroy(comm_stream);
@@ -153,42 +155,45 @@ __global__ void key_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, u
   atomicAdd(hist + b, 1u);
 }
 
-__device__ __forceinline__ uint32_t lower_bound_dev(const uint32_t *__restrict__ keys, uint32_t n, uint32_t z) {
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(keys + mid) < z) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-// bounds[d] = first sorted index with key >= splits[d] (d = 0..world); row[d] = particles bound for rank d;
-// row[world] = particles outside the grid (key >= G), which the last rank owns.
-__global__ void dest_bounds_kernel(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ splits,
-                                   int world, uint32_t G, uint32_t *__restrict__ bounds, uint32_t *__restrict__ row) {
-  __shared__ uint32_t b[kMaxWorld + 2];
-  const int t = threadIdx.x;
-  if (t <= world) b[t] = lower_bound_dev(keys, n, splits[t]);
-  if (t == world + 1) b[t] = lower_bound_dev(keys, n, G);
+// Destination of every owned particle after predict_key: mask[i] = 1 << owner when the owner is another rank, else 0
+// (the same mask format as the ghost lists, so ghost_count_kernel / ghost_scatter_kernel build the leave lists);
+// *n_outside counts particles predicted outside the grid (key >= G), which the last rank owns.
+__global__ void classify_kernel(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ splits_g,
+                                int rank, int world, uint32_t G, uint32_t *__restrict__ mask,
+                                uint32_t *__restrict__ n_outside) {
+  __shared__ uint32_t splits[kMaxWorld + 1];
+  if (threadIdx.x <= (unsigned)world) splits[threadIdx.x] = splits_g[threadIdx.x];
   __syncthreads();
-  if (t <= world) bounds[t] = b[t];
-  if (t < world) row[t] = b[t + 1] - b[t];
-  if (t == world) row[world] = n - b[world + 1];
+  const uint32_t i = blockIdx.x * kBlk + threadIdx.x;
+  const uint32_t key = i < n ? __ldg(keys + i) : 0u;
+  int o = 0;
+  for (int d = 1; d < world; ++d) o += (key >= splits[d]) ? 1 : 0;
+  if (i < n) mask[i] = o == rank ? 0u : 1u << o;
+  const int outside = __syncthreads_count(i < n && key >= G);
+  if (threadIdx.x == 0 && outside) atomicAdd(n_outside, (uint32_t)outside);
 }
 
-__global__ void pack_migrants_kernel(uint32_t n_leave, uint32_t leave_lo, uint32_t n_keep,
-                                     const uint32_t *__restrict__ perm, const float4 *__restrict__ pos,
-                                     const float4 *__restrict__ vel, const float4 *__restrict__ col,
-                                     const unsigned long long *__restrict__ ids, float4 *__restrict__ o_pos,
+// leaving particles, destination-major (leave_idx from ghost_scatter_kernel), raw state + key
+__global__ void pack_migrants_kernel(uint32_t n_leave, const uint32_t *__restrict__ leave_idx,
+                                     const float4 *__restrict__ pos, const float4 *__restrict__ vel,
+                                     const float4 *__restrict__ col, const unsigned long long *__restrict__ ids,
+                                     const uint32_t *__restrict__ keys, float4 *__restrict__ o_pos,
                                      float4 *__restrict__ o_vel, float4 *__restrict__ o_col,
-                                     unsigned long long *__restrict__ o_ids) {
+                                     unsigned long long *__restrict__ o_ids, uint32_t *__restrict__ o_keys) {
   const uint32_t j = blockIdx.x * kBlk + threadIdx.x;
   if (j >= n_leave) return;
-  const uint32_t s = __ldg(perm + (j < leave_lo ? j : j + n_keep));
+  const uint32_t s = __ldg(leave_idx + j);
   o_pos[j] = ldg4(pos + s);
   o_vel[j] = ldg4(vel + s);
   o_col[j] = ldg4(col + s);
   o_ids[j] = __ldg(ids + s);
+  o_keys[j] = __ldg(keys + s);
+}
+
+__global__ void gather_u32_kernel(uint32_t n, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ src,
+                                  uint32_t *__restrict__ out) {
+  const uint32_t i = blockIdx.x * kBlk + threadIdx.x;
+  if (i < n) out[i] = __ldg(src + __ldg(idx + i));
 }
 
 __global__ void iota_kernel(uint32_t *__restrict__ out, uint32_t n, uint32_t first) {
@@ -202,62 +207,83 @@ __device__ __forceinline__ int owner_of(const uint32_t *splits, int world, uint3
   return o;
 }
 
-// Ghost destinations of every owned particle.  radius 2: ranks that need the particle as a ghost (bit d of mask[i]);
-// the first particle of each cell does the 125-cell search and writes the answer for the whole cell.
+// Ghost destinations of every owned particle: bit d of mask[i] = rank d needs particle i as a ghost, i.e. owns a cell
+// within Chebyshev distance 2 of the particle's cell.  The search is per CELL and warp-cooperative: the first particle of
+// each cell is its leader; for every leader in the warp the 32 lanes split the 125 neighbour cells between them and
+// OR-reduce the owners; the leader then writes the answer for its whole cell.
 __global__ void ghost_mask_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t G, int rank, int world,
                                   const uint32_t *__restrict__ splits_g, int any_outside, uint32_t *__restrict__ mask) {
   __shared__ uint32_t splits[kMaxWorld + 1];
   if (threadIdx.x <= (unsigned)world) splits[threadIdx.x] = splits_g[threadIdx.x];
   __syncthreads();
   const uint32_t i = blockIdx.x * kBlk + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t key = __ldg(keys + i);
-  if (i > 0 && __ldg(keys + i - 1) == key) return;
-  uint32_t m = 0;
-  if (key < G) {  // a particle outside the grid is in no cell (sph.hpp:203-213): nobody can see it
-    uint32_t ax[5], ay[5], az[5];
-    const uint32_t kx = key & kAxisMask, ky = (key >> 1) & kAxisMask, kz = (key >> 2) & kAxisMask;
-    ax[2] = kx; ax[1] = dilated_dec(kx); ax[0] = dilated_dec(ax[1]); ax[3] = dilated_inc(kx); ax[4] = dilated_inc(ax[3]);
-    ay[2] = ky; ay[1] = dilated_dec(ky); ay[0] = dilated_dec(ay[1]); ay[3] = dilated_inc(ky); ay[4] = dilated_inc(ay[3]);
-    az[2] = kz; az[1] = dilated_dec(kz); az[0] = dilated_dec(az[1]); az[3] = dilated_inc(kz); az[4] = dilated_inc(az[3]);
-    for (int z = 0; z < 5; ++z)
-      for (int y = 0; y < 5; ++y) {
-        const uint32_t yz = (az[z] << 2) | (ay[y] << 1);
-#pragma unroll
-        for (int x = 0; x < 5; ++x) {
-          const uint32_t nk = yz | ax[x];
-          // a particle predicted outside the grid (key >= G) still walks its 27 cells as `a` (ompsph.hpp:217-232):
-          // those cells matter only while such particles exist
-          if (nk >= G && !any_outside) continue;
-          const int o = owner_of(splits, world, nk);
-          if (o != rank) m |= 1u << o;
-        }
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t key = i < n ? __ldg(keys + i) : 0xFFFFFFFFu;
+  const bool leader = i < n && (i == 0 || __ldg(keys + i - 1) != key);
+  const uint32_t lo = splits[rank], hi = splits[rank + 1];
+  unsigned leaders = __ballot_sync(0xFFFFFFFFu, leader);
+  uint32_t mine = 0;
+  while (leaders) {
+    const int src = __ffs(leaders) - 1;
+    leaders &= leaders - 1;
+    const uint32_t k = __shfl_sync(0xFFFFFFFFu, key, src);
+    uint32_t m = 0;
+    if (k < G) {  // a particle outside the grid is in no cell (sph.hpp:203-213): nobody can see it
+      const uint32_t x = compact10(k), y = compact10(k >> 1), z = compact10(k >> 2);
+      for (uint32_t q = lane; q < 125u; q += 32u) {
+        // offsets -2..+2 with the reference's 10-bit wrap-around (0 - 1 -> 1023, 1023 + 1 -> 0; sph.hpp:221, curves.h:73)
+        const uint32_t nk = morton3((x + q % 5u - 2u) & 1023u, (y + (q / 5u) % 5u - 2u) & 1023u, (z + q / 25u - 2u) & 1023u);
+        // a particle predicted outside the grid (key >= G) still walks its 27 cells as `a` (ompsph.hpp:217-232):
+        // cells >= G matter only while such particles exist
+        if (nk >= G && !any_outside) continue;
+        if (nk < lo || nk >= hi) m |= 1u << owner_of(splits, world, nk);
       }
+    }
+    m = __reduce_or_sync(0xFFFFFFFFu, m);
+    if ((int)lane == src) mine = m;
   }
-  for (uint32_t j = i; j < n && __ldg(keys + j) == key; ++j) mask[j] = m;
+  if (leader)
+    for (uint32_t j = i; j < n && __ldg(keys + j) == key; ++j) mask[j] = mine;
 }
 
-// Ring-1 test for a received ghost: does any of its 27 cells belong to this rank?  (lambda is needed only there)
-__global__ void ghost_ring1_kernel(const uint32_t *__restrict__ keys, uint32_t n_glo, uint32_t n_own, uint32_t n_local,
-                                   uint32_t G, uint32_t lo, uint32_t hi, int any_outside, uint32_t *__restrict__ flag) {
-  const uint32_t t = blockIdx.x * kBlk + threadIdx.x;
-  const uint32_t n_gh = n_local - n_own;
-  if (t >= n_gh) return;
-  const uint32_t i = t < n_glo ? t : t + n_own;
-  const uint32_t key = __ldg(keys + i);
-  const uint32_t kx = key & kAxisMask, ky = (key >> 1) & kAxisMask, kz = (key >> 2) & kAxisMask;
-  const uint32_t ax[3] = {dilated_dec(kx), kx, dilated_inc(kx)};
-  const uint32_t ay[3] = {dilated_dec(ky), ky, dilated_inc(ky)};
-  const uint32_t az[3] = {dilated_dec(kz), kz, dilated_inc(kz)};
+// Role of every particle of the local array for the solver passes (static within a step):
+//   kRoleLambda    lambda is computed here: owned particles and RING-1 ghosts (a ghost one of whose 27 cells is ours)
+//   kRoleBoundary  owned, and some other rank holds it as a ghost: its delta pass runs first so the halo can leave
+//   kRoleInterior  owned, nobody else needs it: its delta pass overlaps the halo exchange
+// counts[0] += ring-1 ghosts, counts[1] += boundary particles (statistics only).
+constexpr uint32_t kRoleLambda = 1u, kRoleBoundary = 2u, kRoleInterior = 4u;
+__global__ void roles_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ owned_mask, uint32_t n_glo,
+                             uint32_t n_own, uint32_t n_local, uint32_t G, uint32_t lo, uint32_t hi, int any_outside,
+                             uint32_t *__restrict__ role, uint32_t *__restrict__ counts) {
+  const uint32_t i = blockIdx.x * kBlk + threadIdx.x;
   uint32_t f = 0;
-  for (int z = 0; z < 3; ++z)
-    for (int y = 0; y < 3; ++y)
-      for (int x = 0; x < 3; ++x) {
-        const uint32_t nk = (az[z] << 2) | (ay[y] << 1) | ax[x];
-        if (nk >= G && !any_outside) continue;
-        f |= (nk >= lo && nk < hi) ? 1u : 0u;
-      }
-  flag[i] = f;
+  bool ring1 = false, boundary = false;
+  if (i < n_local) {
+    if (i >= n_glo && i < n_glo + n_own) {
+      boundary = __ldg(owned_mask + (i - n_glo)) != 0u;
+      f = kRoleLambda | (boundary ? kRoleBoundary : kRoleInterior);
+    } else {
+      const uint32_t key = __ldg(keys + i);
+      const uint32_t kx = key & kAxisMask, ky = (key >> 1) & kAxisMask, kz = (key >> 2) & kAxisMask;
+      const uint32_t ax[3] = {dilated_dec(kx), kx, dilated_inc(kx)};
+      const uint32_t ay[3] = {dilated_dec(ky), ky, dilated_inc(ky)};
+      const uint32_t az[3] = {dilated_dec(kz), kz, dilated_inc(kz)};
+      for (int z = 0; z < 3; ++z)
+        for (int y = 0; y < 3; ++y)
+          for (int x = 0; x < 3; ++x) {
+            const uint32_t nk = (az[z] << 2) | (ay[y] << 1) | ax[x];
+            if (nk >= G && !any_outside) continue;
+            ring1 |= nk >= lo && nk < hi;
+          }
+      f = ring1 ? kRoleLambda : 0u;
+    }
+    role[i] = f;
+  }
+  const int c_ring1 = __syncthreads_count(ring1), c_boundary = __syncthreads_count(boundary);
+  if (threadIdx.x == 0) {
+    if (c_ring1) atomicAdd(counts, (uint32_t)c_ring1);
+    if (c_boundary) atomicAdd(counts + 1, (uint32_t)c_boundary);
+  }
 }
 
 // Per 256-particle tile and destination: how many particles go there (cnt[d * nblk + blk]); totals into row[d].
@@ -452,22 +478,22 @@ void plan_splits(const uint64_t *hist, uint32_t n_buckets, uint32_t shift, int w
   splits[world] = kKeyEnd;
 }
 
-// stable compaction of flag[first .. first+n) -> out (indices); the count lands in c->mc_total_host[slot] (slot 1..3)
-int compact_flags(pbf_ctx *c, const uint32_t *flag, uint32_t first, uint32_t n, uint32_t want, DevBuf<uint32_t> &out,
-                  int slot) {
+// stable compaction of the indices first+t with (flag[first+t] != 0) == want into out[]; with slot > 0 the count is
+// also copied to c->mc_total_host[slot] (slot 1..3; read it after synchronising the stream)
+int compact_flags(pbf_ctx *c, const uint32_t *flag, uint32_t first, uint32_t n, uint32_t want, uint32_t *out, int slot) {
   D *d = c->dist;
-  c->mc_total_host[slot] = 0;
+  if (slot > 0) c->mc_total_host[slot] = 0;
   if (n == 0) return PBF_OK;
   const uint32_t nblk = div_up(n, kBlk);
   PBF_CUDA(c, d->sub_cnt.reserve(nblk + 4));
-  PBF_CUDA(c, out.reserve(n));
   flag_count_kernel<<<nblk, kBlk, 0, c->stream>>>(flag, first, n, want, d->sub_cnt.p);
   PBF_LAUNCH_CHECK(c);
-  PBF_TRY(exclusive_scan_u32(c, d->sub_cnt.p, d->sub_cnt.p, nblk, c->mc_total_dev + slot));
-  flag_scatter_kernel<<<nblk, kBlk, 0, c->stream>>>(flag, first, n, want, d->sub_cnt.p, out.p);
+  PBF_TRY(exclusive_scan_u32(c, d->sub_cnt.p, d->sub_cnt.p, nblk, slot > 0 ? c->mc_total_dev + slot : nullptr));
+  flag_scatter_kernel<<<nblk, kBlk, 0, c->stream>>>(flag, first, n, want, d->sub_cnt.p, out);
   PBF_LAUNCH_CHECK(c);
-  PBF_CUDA(c, cudaMemcpyAsync(c->mc_total_host + slot, c->mc_total_dev + slot, 4, cudaMemcpyDeviceToHost, c->stream));
-  return PBF_OK;  // the caller synchronises the stream before reading mc_total_host[slot]
+  if (slot > 0)
+    PBF_CUDA(c, cudaMemcpyAsync(c->mc_total_host + slot, c->mc_total_dev + slot, 4, cudaMemcpyDeviceToHost, c->stream));
+  return PBF_OK;
 }
 
 // ------------------------------------------------------------------------------------------------- the phases
@@ -513,37 +539,48 @@ int phase_plan(pbf_ctx *c) {
   return PBF_OK;
 }
 
+// classify the owned particles by destination rank; counts per destination into d_row (x1 gathers the rows)
 int phase_a2(pbf_ctx *c) {
   D *d = c->dist;
+  const int W = d->world;
   PBF_CUDA(c, cudaSetDevice(c->device));
-  c->sc.n = d->n_in;
-  PBF_TRY(radix_sort_pairs(c, c->key_in.p, d->n_in));
+  PBF_CUDA(c, cudaMemsetAsync(d->d_row.p, 0, (W + 1) * 4, c->stream));
+  if (d->n_in == 0) return PBF_OK;
   PhaseScope ps(c, PBF_PH_HALO);
-  dest_bounds_kernel<<<1, 64, 0, c->stream>>>(c->keys_sorted, d->n_in, d->d_splits.p, d->world, c->sc.G, d->d_bounds.p, d->d_row.p);
+  const uint32_t nblk = div_up(d->n_in, kBlk);
+  PBF_CUDA(c, d->mask.reserve(d->n_in));
+  PBF_CUDA(c, d->blk_cnt.reserve((size_t)W * nblk + 4));
+  classify_kernel<<<nblk, kBlk, 0, c->stream>>>(c->key_in.p, d->n_in, d->d_splits.p, d->rank, W, c->sc.G, d->mask.p, d->d_row.p + W);
+  PBF_LAUNCH_CHECK(c);
+  ghost_count_kernel<<<nblk, kBlk, 0, c->stream>>>(d->mask.p, d->n_in, W, nblk, d->blk_cnt.p, d->d_row.p);
   PBF_LAUNCH_CHECK(c);
   return PBF_OK;
 }
 
-// after x1: read the migration matrix, pack the leaving particles, describe the all-to-all
+// after x1: read the migration matrix (row s, column t = particles going from s to t; the diagonal is unused, column W =
+// particles outside the grid), pack the leaving particles, describe the all-to-all
 int phase_b(pbf_ctx *c) {
   D *d = c->dist;
   const int W = d->world, r = d->rank, RW = W + 1;
   PBF_CUDA(c, cudaSetDevice(c->device));
-  uint32_t *M = d->h_pinned, *hb = d->h_pinned + (size_t)W * RW;
+  uint32_t *M = d->h_pinned;
   PBF_CUDA(c, cudaMemcpyAsync(M, d->d_all.p, (size_t)W * RW * 4, cudaMemcpyDeviceToHost, c->stream));
-  PBF_CUDA(c, cudaMemcpyAsync(hb, d->d_bounds.p, (W + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
   PBF_CUDA(c, cudaStreamSynchronize(c->stream));
-  d->bounds.assign(hb, hb + W + 1);
-  d->n_keep = M[r * RW + r];
-  d->total_out = d->n_in - d->n_keep;
+  d->total_out = 0;
   d->total_in = 0;
+  d->in_lo = 0;
   uint64_t off_diag = 0, outside = 0;
   for (int s = 0; s < W; ++s) {
     outside += M[s * RW + W];
     for (int t = 0; t < W; ++t)
       if (s != t) off_diag += M[s * RW + t];
-    if (s != r) d->total_in += M[s * RW + r];
+    if (s != r) {
+      d->total_in += M[s * RW + r];
+      d->total_out += M[r * RW + s];
+      if (s < r) d->in_lo += M[s * RW + r];
+    }
   }
+  d->n_keep = d->n_in - d->total_out;
   d->any_migrants = off_diag != 0;
   d->any_outside = outside != 0;
   d->n_own = d->n_keep + d->total_in;
@@ -559,14 +596,20 @@ int phase_b(pbf_ctx *c) {
   PBF_CUDA(c, d->sb_b.reserve(d->total_out + 1));
   PBF_CUDA(c, d->sb_c.reserve(d->total_out + 1));
   PBF_CUDA(c, d->sb_id.reserve(d->total_out + 1));
+  PBF_CUDA(c, d->sb_key.reserve(d->total_out + 1));
+  PBF_CUDA(c, d->send_idx.reserve(d->total_out + 1));
   PBF_CUDA(c, d->k2.reserve(d->n_own + 1));
   PBF_CUDA(c, d->v2.reserve(d->n_own + 1));
   float4 *pin = c->pos[c->cur].p + d->own_off, *vin = c->vel[c->cur].p + d->own_off, *cin = c->col[c->cur_col].p + d->own_off;
   unsigned long long *iin = c->ids[c->cur].p + d->own_off;
   if (d->total_out) {
     PhaseScope ps(c, PBF_PH_HALO);
-    pack_migrants_kernel<<<div_up(d->total_out, kBlk), kBlk, 0, c->stream>>>(
-        d->total_out, d->bounds[r], d->n_keep, c->perm, pin, vin, cin, iin, d->sb_a.p, d->sb_b.p, d->sb_c.p, d->sb_id.p);
+    const uint32_t nblk = div_up(d->n_in, kBlk);
+    PBF_TRY(exclusive_scan_u32(c, d->blk_cnt.p, d->blk_cnt.p, (uint64_t)W * nblk, nullptr));
+    ghost_scatter_kernel<<<nblk, kBlk, 0, c->stream>>>(d->mask.p, d->n_in, W, nblk, d->blk_cnt.p, d->send_idx.p);
+    PBF_LAUNCH_CHECK(c);
+    pack_migrants_kernel<<<div_up(d->total_out, kBlk), kBlk, 0, c->stream>>>(d->total_out, d->send_idx.p, pin, vin, cin, iin, c->key_in.p,
+                                                                          d->sb_a.p, d->sb_b.p, d->sb_c.p, d->sb_id.p, d->sb_key.p);
     PBF_LAUNCH_CHECK(c);
   }
   d->msgs.resize(5);
@@ -574,54 +617,52 @@ int phase_b(pbf_ctx *c) {
   d->msgs[1].init(W, d->sb_b.p, vin + d->n_in, 16);
   d->msgs[2].init(W, d->sb_c.p, cin + d->n_in, 16);
   d->msgs[3].init(W, d->sb_id.p, iin + d->n_in, 8);
-  d->msgs[4].init(W, c->keys_sorted, d->k2.p, 4);  // keys arrive in merge order: [from lower ranks | kept | from higher ranks]
+  d->msgs[4].init(W, d->sb_key.p, d->k2.p, 4);  // keys arrive in merge order: [from lower ranks | kept | from higher ranks]
   // Arrival order = source-rank order, with the kept particles between the lower and the higher ranks: when the
-  // ranks' inputs are consecutive blocks of one array (dist.py shard()), the merged stable sort then reproduces the
-  // single-GPU stable order exactly, cell by cell.
-  d->in_lo = 0;
-  for (int q = 0; q < r; ++q) d->in_lo += M[q * RW + r];
-  uint64_t roff = 0;
+  // ranks' inputs are consecutive blocks of one array (dist.py shard()), the stable sort of that sequence reproduces
+  // the single-GPU stable order exactly, cell by cell.
+  uint64_t soff = 0, roff = 0;
   for (int q = 0; q < W; ++q) {
     if (q == r) continue;
     const uint64_t sc = M[r * RW + q], rc = M[q * RW + r];
-    const uint64_t soff_packed = q < r ? d->bounds[q] : d->bounds[q] - d->n_keep;
     for (int k = 0; k < 5; ++k) {
       Msg &m = d->msgs[k];
       m.send_cnt[q] = sc;
-      m.send_off[q] = k == 4 ? d->bounds[q] : soff_packed;
+      m.send_off[q] = soff;
       m.recv_cnt[q] = rc;
       m.recv_off[q] = (k == 4 && q > r) ? roff + d->n_keep : roff;
     }
+    soff += sc;
     roff += rc;
   }
   return PBF_OK;
 }
 
-// after x2: merge the arrivals, find the ghost destinations of every owned particle
+// after x2: ONE stable sort of [arrivals from lower ranks | kept | arrivals from higher ranks]; then the ghost
+// destinations of every owned particle
 int phase_c(pbf_ctx *c) {
   D *d = c->dist;
   const int W = d->world, r = d->rank;
   PBF_CUDA(c, cudaSetDevice(c->device));
+  c->sc.n = d->n_own;
   if (d->any_migrants) {
-    if (d->total_in) {
-      const uint32_t in_hi = d->total_in - d->in_lo;
-      if (d->n_keep) {
-        PBF_CUDA(c, cudaMemcpyAsync(d->k2.p + d->in_lo, c->keys_sorted + d->bounds[r], (size_t)d->n_keep * 4, cudaMemcpyDeviceToDevice, c->stream));
-        PBF_CUDA(c, cudaMemcpyAsync(d->v2.p + d->in_lo, c->perm + d->bounds[r], (size_t)d->n_keep * 4, cudaMemcpyDeviceToDevice, c->stream));
-      }
-      if (d->in_lo) {  // the arrivals sit behind the owned particles of the input arrays, in source-rank order
-        iota_kernel<<<div_up(d->in_lo, kBlk), kBlk, 0, c->stream>>>(d->v2.p, d->in_lo, d->n_in);
-        PBF_LAUNCH_CHECK(c);
-      }
-      if (in_hi) {
-        iota_kernel<<<div_up(in_hi, kBlk), kBlk, 0, c->stream>>>(d->v2.p + d->in_lo + d->n_keep, in_hi, d->n_in + d->in_lo);
-        PBF_LAUNCH_CHECK(c);
-      }
-      PBF_TRY(radix_sort_pairs(c, d->k2.p, d->n_own, d->v2.p));
-    } else {  // nothing arrived: the kept segment of the first sort is the owned set
-      c->keys_sorted += d->bounds[r];
-      c->perm += d->bounds[r];
+    const uint32_t in_hi = d->total_in - d->in_lo;
+    if (d->n_keep) {  // kept = mask 0, in input order; their keys gathered behind the lower ranks' arrivals
+      PBF_TRY(compact_flags(c, d->mask.p, 0, d->n_in, 0, d->v2.p + d->in_lo, 0));
+      gather_u32_kernel<<<div_up(d->n_keep, kBlk), kBlk, 0, c->stream>>>(d->n_keep, d->v2.p + d->in_lo, c->key_in.p, d->k2.p + d->in_lo);
+      PBF_LAUNCH_CHECK(c);
     }
+    if (d->in_lo) {  // the arrivals sit behind the owned particles of the input arrays, in source-rank order
+      iota_kernel<<<div_up(d->in_lo, kBlk), kBlk, 0, c->stream>>>(d->v2.p, d->in_lo, d->n_in);
+      PBF_LAUNCH_CHECK(c);
+    }
+    if (in_hi) {
+      iota_kernel<<<div_up(in_hi, kBlk), kBlk, 0, c->stream>>>(d->v2.p + d->in_lo + d->n_keep, in_hi, d->n_in + d->in_lo);
+      PBF_LAUNCH_CHECK(c);
+    }
+    PBF_TRY(radix_sort_pairs(c, d->k2.p, d->n_own, d->v2.p));
+  } else {
+    PBF_TRY(radix_sort_pairs(c, c->key_in.p, d->n_in));
   }
   c->n = d->n_own;
   PBF_CUDA(c, cudaMemsetAsync(d->d_row.p, 0, (W + 1) * 4, c->stream));
@@ -673,7 +714,6 @@ int phase_d(pbf_ctx *c) {
   PBF_CUDA(c, d->sb_a.reserve(d->n_send + 1));
   PBF_CUDA(c, d->sb_b.reserve(d->n_send + 1));
   PBF_CUDA(c, d->sb_key.reserve(d->n_send + 1));
-  d->n_boundary = 0;
   if (d->n_own) {
     c->sc.n = d->n_own;
     PBF_TRY(launch_reorder(c, c->perm, c->pos[c->cur].p + d->own_off, c->vel[c->cur].p + d->own_off,
@@ -722,7 +762,6 @@ int phase_e(pbf_ctx *c) {
   c->sc.n = d->n_local;
   c->grid.n_particles = d->n_local;
   c->keys_sorted = d->keys_local.p;
-  d->n_ring1 = 0;
   if (d->n_local == 0) return PBF_OK;
   if (n_gh) {
     PhaseScope ps(c, PBF_PH_HALO);
@@ -731,26 +770,15 @@ int phase_e(pbf_ctx *c) {
   }
   PBF_TRY(launch_cell_table(c, c->keys_sorted, c->table.p));
   {
-    // subsets (static for the step): lambda runs on owned + ring-1 ghosts; delta on boundary first, interior second
     PhaseScope ps(c, PBF_PH_HALO);
-    // mask[] holds the destination masks of the owned particles (owned indexing): non-zero = boundary
-    PBF_TRY(compact_flags(c, d->mask.p, 0, d->n_own, 1, d->sub_boundary, 1));
-    PBF_TRY(compact_flags(c, d->mask.p, 0, d->n_own, 0, d->sub_interior, 2));
-    c->mc_total_host[3] = d->n_own;
-    if (n_gh) {
-      // ring-1 flags over the ghost ranges, owned range flagged 1
-      PBF_CUDA(c, d->v2.reserve(d->n_local));
-      PBF_CUDA(c, cudaMemsetAsync(d->v2.p, 0xFF, (size_t)d->n_local * 4, c->stream));
-      ghost_ring1_kernel<<<div_up(n_gh, kBlk), kBlk, 0, c->stream>>>(c->keys_sorted, d->n_glo, d->n_own, d->n_local, c->sc.G,
-                                                                    d->splits[d->rank], d->splits[d->rank + 1], d->any_outside ? 1 : 0, d->v2.p);
-      PBF_LAUNCH_CHECK(c);
-      PBF_TRY(compact_flags(c, d->v2.p, 0, d->n_local, 1, d->sub_lambda, 3));
-    }
-    PBF_CUDA(c, cudaStreamSynchronize(c->stream));
-    d->n_boundary = c->mc_total_host[1];
-    if (d->n_boundary + c->mc_total_host[2] != d->n_own)
-      return fail(c, PBF_ERR_STATE, "pbf_dist_step", "boundary/interior split lost particles");
-    d->n_ring1 = c->mc_total_host[3] - d->n_own;
+    PBF_CUDA(c, d->role.reserve(d->n_local));
+    PBF_CUDA(c, cudaMemsetAsync(c->mc_total_dev + 1, 0, 8, c->stream));
+    roles_kernel<<<div_up(d->n_local, kBlk), kBlk, 0, c->stream>>>(c->keys_sorted, d->mask.p, d->n_glo, d->n_own, d->n_local, c->sc.G,
+                                                                  d->splits[d->rank], d->splits[d->rank + 1], d->any_outside ? 1 : 0,
+                                                                  d->role.p, c->mc_total_dev + 1);
+    PBF_LAUNCH_CHECK(c);
+    // statistics only: read after the next synchronisation (pbf_dist_stats_read)
+    PBF_CUDA(c, cudaMemcpyAsync(c->mc_total_host + 1, c->mc_total_dev + 1, 8, cudaMemcpyDeviceToHost, c->stream));
   }
   if (c->flags & PBF_FLAG_DEBUG_COUNTS) {
     PBF_CUDA(c, c->cand_count.reserve(d->n_local));
@@ -799,35 +827,31 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
       if (d->n_local == 0) continue;
       c->sc.n = d->n_local;
       float *rho = it + 1 == p.iteration ? c->rho.p : nullptr;
+      const bool have_ghosts = d->n_glo + d->n_ghi != 0;
       {
         PhaseScope ps(c, PBF_PH_LAMBDA);
-        if (d->n_glo + d->n_ghi)
-          PBF_TRY(launch_lambda_list(c, 0, d->n_own + d->n_ring1, c->keys_sorted, c->table.p, c->pos[c->cur].p, c->pstar[0].p,
-                                     c->pstar[1].p, rho, d->sub_lambda.p));
-        else
-          PBF_TRY(launch_lambda_list(c, 0, d->n_local, c->keys_sorted, c->table.p, c->pos[c->cur].p, c->pstar[0].p, c->pstar[1].p, rho, nullptr));
+        PBF_TRY(launch_lambda_list(c, 0, d->n_local, c->keys_sorted, c->table.p, c->pos[c->cur].p, c->pstar[0].p, c->pstar[1].p, rho,
+                                   have_ghosts ? d->role.p : nullptr, kRoleLambda));
       }
       if (d->n_own == 0) continue;
-      if (exchange && d->n_boundary) {
+      if (exchange && d->n_send) {
         // boundary particles first; their halo goes out on the comm stream while the interior pass runs
         {
           PhaseScope ps(c, PBF_PH_DELTA);
-          PBF_TRY(launch_delta_list(c, 0, d->n_boundary, c->keys_sorted, c->table.p, c->pstar[1].p, c->pstar[0].p, d->sub_boundary.p, d->own_off));
+          PBF_TRY(launch_delta_list(c, d->own_off, d->n_own, c->keys_sorted, c->table.p, c->pstar[1].p, c->pstar[0].p, d->role.p, kRoleBoundary));
         }
         PBF_CUDA(c, cudaEventRecord(d->ev_boundary, c->stream));
         PBF_CUDA(c, cudaStreamWaitEvent(d->comm_stream, d->ev_boundary, 0));
-        if (d->n_send) {
-          pack_pstar_kernel<<<div_up(d->n_send, kBlk), kBlk, 0, d->comm_stream>>>(d->n_send, d->own_off, d->send_idx.p, c->pstar[0].p, d->sb_a.p);
-          PBF_LAUNCH_CHECK(c);
-        }
+        pack_pstar_kernel<<<div_up(d->n_send, kBlk), kBlk, 0, d->comm_stream>>>(d->n_send, d->own_off, d->send_idx.p, c->pstar[0].p, d->sb_a.p);
+        PBF_LAUNCH_CHECK(c);
         {
           PhaseScope ps(c, PBF_PH_DELTA);
-          PBF_TRY(launch_delta_list(c, 0, d->n_own - d->n_boundary, c->keys_sorted, c->table.p, c->pstar[1].p, c->pstar[0].p, d->sub_interior.p, d->own_off));
+          PBF_TRY(launch_delta_list(c, d->own_off, d->n_own, c->keys_sorted, c->table.p, c->pstar[1].p, c->pstar[0].p, d->role.p, kRoleInterior));
         }
       } else {
         PhaseScope ps(c, PBF_PH_DELTA);
         PBF_TRY(launch_delta_list(c, d->own_off, d->n_own, c->keys_sorted, c->table.p, c->pstar[1].p, c->pstar[0].p, nullptr, 0));
-        if (exchange) {  // a rank without boundary particles still takes part in the exchange
+        if (exchange) {  // a rank that sends nothing still takes part in the exchange
           PBF_CUDA(c, cudaEventRecord(d->ev_boundary, c->stream));
           PBF_CUDA(c, cudaStreamWaitEvent(d->comm_stream, d->ev_boundary, 0));
         }
@@ -864,8 +888,6 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
     d->stats.halo_bytes_per_iteration = (uint64_t)d->n_send * 16;
     d->stats.key_lo = d->splits[d->rank];
     d->stats.key_hi = d->splits[d->rank + 1];
-    d->stats.ghost_ring1 = d->n_ring1;
-    d->stats.boundary = d->n_boundary;
   }
   return PBF_OK;
 }
@@ -879,7 +901,6 @@ int dist_alloc(pbf_ctx *c, int rank, int world) {
   c->dist = d;
   PBF_CUDA(c, cudaSetDevice(c->device));
   PBF_CUDA(c, d->d_splits.reserve(world + 2));
-  PBF_CUDA(c, d->d_bounds.reserve(world + 2));
   PBF_CUDA(c, d->d_row.reserve(world + 2));
   PBF_CUDA(c, d->d_all.reserve((size_t)world * (world + 1) + 2));
   PBF_CUDA(c, cudaHostAlloc(&d->h_pinned, ((size_t)(world + 1) * (world + 2) + 64) * 4, cudaHostAllocDefault));
@@ -984,7 +1005,11 @@ int pbf_dist_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_
 
 int pbf_dist_stats_read(pbf_ctx *ctx, pbf_dist_stats *out) {
   if (!ctx || !ctx->dist || !out) return fail(ctx, PBF_ERR_STATE, "pbf_dist_stats_read", "pbf_dist_init first");
+  PBF_CUDA(ctx, cudaSetDevice(ctx->device));
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *out = ctx->dist->stats;
+  out->ghost_ring1 = ctx->mc_total_host[1];
+  out->boundary = ctx->mc_total_host[2];
   return PBF_OK;
 }
 

@@ -40,10 +40,11 @@ __global__ void __launch_bounds__(kBlock) lambda_list_kernel(StepConst c, uint32
                                                              const float4 *__restrict__ pstar_in,
                                                              float4 *__restrict__ pstar_out, float *__restrict__ rho_out,
                                                              uint32_t *nl, uint32_t stride, uint32_t *__restrict__ n_hits,
-                                                             const uint32_t *__restrict__ subset, uint32_t subset_base) {
+                                                             const uint32_t *__restrict__ role, uint32_t want) {
   const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
   if (t >= count) return;
-  const uint32_t a = subset ? subset_base + __ldg(subset + t) : first + t;
+  const uint32_t a = first + t;
+  if (role && !(__ldg(role + a) & want)) return;  // multi-GPU: not this pass's particle (dist.cu roles)
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t key = __ldg(keys + a);
   const float mass = __ldg(&pos_mass[a].w);
@@ -86,10 +87,11 @@ __global__ void __launch_bounds__(kBlock) delta_list_kernel(StepConst c, uint32_
                                                             float4 *__restrict__ pstar_out,
                                                             const uint32_t *__restrict__ nl, uint32_t stride,
                                                             const uint32_t *__restrict__ n_hits,
-                                                            const uint32_t *__restrict__ subset, uint32_t subset_base) {
+                                                            const uint32_t *__restrict__ role, uint32_t want) {
   const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
   if (t >= count) return;
-  const uint32_t a = subset ? subset_base + __ldg(subset + t) : first + t;
+  const uint32_t a = first + t;
+  if (role && !(__ldg(role + a) & want)) return;  // multi-GPU: not this pass's particle (dist.cu roles)
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t k = __ldg(n_hits + a);
   DeltaAcc<kStrict> acc;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kBlock) delta_list_kernel(StepConst c, uint32_
 
 int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                        const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
-                       const uint32_t *subset, uint32_t subset_base) {
+                       const uint32_t *role, uint32_t want) {
   if (count == 0) return PBF_OK;
   const uint32_t n = ctx->sc.n;
   const uint32_t stride = (n + 31u) & ~31u;  // rows start on 128-byte boundaries
@@ -122,26 +124,26 @@ int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint3
   if (ctx->flags & PBF_FLAG_STRICT_FP)
     lambda_list_kernel<true><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
         ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, ctx->nl.p, stride, ctx->nl_count.p,
-        subset, subset_base);
+        role, want);
   else
     lambda_list_kernel<false><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
         ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, ctx->nl.p, stride, ctx->nl_count.p,
-        subset, subset_base);
+        role, want);
   PBF_LAUNCH_CHECK(ctx);
   return PBF_OK;
 }
 
 int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                      const float4 *pstar_in, float4 *pstar_out, const uint32_t *subset, uint32_t subset_base) {
+                      const float4 *pstar_in, float4 *pstar_out, const uint32_t *role, uint32_t want) {
   if (count == 0) return PBF_OK;
   if (ctx->flags & PBF_FLAG_STRICT_FP)
     delta_list_kernel<true><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
         ctx->sc, first, count, keys_sorted, table, pstar_in, pstar_out, ctx->nl.p, ctx->nl_stride, ctx->nl_count.p,
-        subset, subset_base);
+        role, want);
   else
     delta_list_kernel<false><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
         ctx->sc, first, count, keys_sorted, table, pstar_in, pstar_out, ctx->nl.p, ctx->nl_stride, ctx->nl_count.p,
-        subset, subset_base);
+        role, want);
   PBF_LAUNCH_CHECK(ctx);
   return PBF_OK;
 }
