@@ -1,0 +1,54 @@
+"""The `benchmark` driver (src/benchmark.cpp): the reference's flags and summary lines (reference benchmark.cpp:91-101,
+args.cpp:7-50) through the C++ adaptor sph::cuda_impl::Solver (include/pbf/cudasph.hpp) — i.e. the C++ host path of the
+drop-in boundary, including Result/mesh hand-off and the cloud.ply / mesh.obj writers."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from pbf_sph_b200 import Solver, scenes
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+EXE = ROOT / "build" / "benchmark"
+
+
+def run(*args):
+    if not EXE.exists():
+        subprocess.run(["make", "-C", str(ROOT / "pbf_sph_b200" / "csrc")], check=True, capture_output=True)
+    return subprocess.run([str(EXE), *args], capture_output=True, text=True, timeout=300)
+
+
+def test_benchmark_stock_scene_matches_python_mirror(gpu, tmp_path):
+    out = run("-i", "cuda", "-n", "4", "-w", "3", "-o", str(tmp_path / "out_{impl}_{type}_{iter}"))
+    assert out.returncode == 0, out.stderr
+    for label in ("Benchmark completed after 4 frames", "Runtime", "Framerate", "Frame-time min", "Frame-time max",
+                  "Frame-time mean", "Frame-time stdDev", "Final Vertex count", "Final Particle count : 18522", "Results flushed."):
+        assert label in out.stdout, out.stdout
+    d = tmp_path / "out_cuda_fp32_4"
+    assert (d / "cloud.ply").exists() and (d / "mesh.obj").exists()
+    # the same frames through the Python mirror of the same C ABI: identical final particles
+    p, xs = scenes.two_cubes(20000, 6)
+    p.surface_enabled = 1
+    with Solver(scenes.H, 0) as s:
+        for f in list(range(3)) + list(range(4)):  # warm-up frames 0..2, then timed frames 0..3 (benchmark.cpp:31-54)
+            res = s.advance(scenes.apply_motion(p, f), xs)
+    raw = (d / "cloud.ply").read_bytes()
+    body = raw[raw.index(b"end_header\n") + len(b"end_header\n"):]
+    rec = np.frombuffer(body, dtype=np.dtype([("xyz", "<f4", 3), ("rgba", "<f4", 4), ("id", "<u4")]))
+    assert len(rec) == len(xs)
+    assert np.array_equal(rec["id"], xs["id"].astype(np.uint32))
+    assert np.array_equal(rec["xyz"], xs["position"])
+    nv = int(re.search(r"Final Vertex count\s*:\s*(\d+)", out.stdout).group(1))
+    assert nv == len(res.vs) and nv > 1000
+    assert sum(1 for line in (d / "mesh.obj").read_text().splitlines() if line.startswith("v ")) == nv
+
+
+def test_benchmark_flags(gpu, tmp_path):
+    assert run("--fp64").returncode != 0                      # fp32 only, like the OpenCL backend
+    assert run("-i", "omp").returncode != 0
+    assert "CUDA device 0" in run("-l").stdout
+    out = run("--scene=dam", "--particles=27000", "--solver-iters=4", "--surface=off", "--resident", "-n3", "-w2", "-o", "")
+    assert out.returncode == 0 and "Final Particle count : 27000" in out.stdout and "Final Vertex count   : 0" in out.stdout
