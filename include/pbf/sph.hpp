@@ -158,8 +158,16 @@ std::tuple<McParams<N>, SphParams<T, N, V>, std::vector<Particle<T, N, V>>> damB
   const N lx = N(44) * N(side) + N(200), ly = N(22) * N(side) + N(200);
   auto c = defaultParams<T, N, V>(solverIter, scaling);
   c.maxBound = V<3>(lx, ly, ly);
+  // (not makeCube: its side = (size_t)cbrt(count) rounds 30^3 down to 29, like the reference's would)
   std::vector<Particle<T, N, V>> xs;
-  makeCube<T, N, V>(T{}, N(22), side * side * side, V<3>(100, ly - N(22) * N(side) - N(50), 100), V<4>(0, 0.1, 0.8, 1), xs);
+  xs.reserve(side * side * side);
+  const V<3> origin(100, ly - N(22) * N(side) - N(50), 100);
+  T id{};
+  for (size_t x = 0; x < side; ++x)
+    for (size_t y = 0; y < side; ++y)
+      for (size_t z = 0; z < side; ++z)
+        xs.emplace_back(id++, Type::Fluid, N(1), V<4>(0, 0.1, 0.8, 1),
+                        V<3>(N(x) * N(22) + origin.x, N(y) * N(22) + origin.y, N(z) * N(22) + origin.z), V<3>(0, 0, 0));
   return {McParams<N>{N(2), N(100), N(25), N(0.5)}, c, xs};
 }
 

@@ -87,7 +87,7 @@ enum {
   PBF_FLAG_STRICT_FP = 1u << 0,    /* no FMA contraction, IEEE div/sqrt in the solver kernels: follows the oracle op-for-op */
   PBF_FLAG_DEBUG_COUNTS = 1u << 1, /* also run the neighbour-count tap each step (PBF_TAP_CAND_COUNT/NBR_COUNT) */
   PBF_FLAG_PROFILE = 1u << 2,      /* record CUDA events around every kernel family (pbf_profile_read) */
-  PBF_FLAG_GLOBAL_NEIGHBOURS = 1u << 3 /* use the un-tiled global-memory neighbour kernels (A/B testing) */
+  PBF_FLAG_GLOBAL_NEIGHBOURS = 1u << 3 /* use the one-pass global-memory neighbour kernels (A/B testing) */
 };
 
 /* Debug taps, all in SORTED particle order unless stated (pbf_debug_read). */

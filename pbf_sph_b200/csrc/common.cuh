@@ -178,6 +178,7 @@ struct pbf_ctx {
   // per-iteration neighbour list: nl[k * nl_stride + particle] = k-th in-radius candidate, nl_count[particle] = hits
   pbf::DevBuf<uint32_t> nl, nl_count;
   uint32_t nl_stride = 0;
+  int list_cap = 96;  // hits kept per particle in the neighbour list (kListMax, or 64 via PBF_LIST_CAP for A/B runs)
 
   pbf_grid_info grid{};
   pbf::StepConst sc{};
@@ -252,13 +253,19 @@ int launch_lambda_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uin
 int launch_delta_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
                         const uint32_t *table, const float4 *pstar_in, float4 *pstar_out);
 // neighbour-list kernels (neighbour_list.cu): the production lambda/delta passes
-constexpr uint32_t kListMax = 64;  // hits stored per particle; beyond that the particle takes the one-pass path
+constexpr uint32_t kListMax = 96;  // hits stored per particle; beyond that the particle takes the one-pass path
 int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                        const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
                        const uint32_t *role = nullptr, uint32_t want = 0);
 // role != nullptr: particle a is processed only when role[a] & want (multi-GPU: ring-1 / boundary / interior, dist.cu)
 int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                       const float4 *pstar_in, float4 *pstar_out, const uint32_t *role = nullptr, uint32_t want = 0);
+// The production lambda / delta pass over the sorted range [first, first + count) (neighbour-list kernels, or the
+// one-pass global kernels under PBF_FLAG_GLOBAL_NEIGHBOURS).
+int solver_lambda(pbf_ctx *ctx, uint32_t first, uint32_t count, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
+                  const uint32_t *role = nullptr, uint32_t want = 0);
+int solver_delta(pbf_ctx *ctx, uint32_t first, uint32_t count, const float4 *pstar_in, float4 *pstar_out,
+                 const uint32_t *role = nullptr, uint32_t want = 0);
 // shared-memory tiled colour diffusion (diffuse_tiled.cu)
 int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *col_in,
                          float4 *col_out);

@@ -8,6 +8,7 @@
 // point converts from/to the reference's 56-byte AoS records on the device.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -121,19 +122,21 @@ static void profile_collect(pbf_ctx *ctx) {
 }
 
 // ---- the step ------------------------------------------------------------------------------------------------------
-static int lambda_pass(pbf_ctx *ctx, const float4 *pstar_in, float4 *pstar_out, float *rho_out) {
+int solver_lambda(pbf_ctx *ctx, uint32_t first, uint32_t count, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
+                  const uint32_t *role, uint32_t want) {
   PhaseScope ps(ctx, PBF_PH_LAMBDA);
-  if (!(ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS))
-    return launch_lambda_list(ctx, 0, ctx->sc.n, ctx->keys_sorted, ctx->table.p, ctx->pos[ctx->cur].p, pstar_in,
-                              pstar_out, rho_out);
-  return launch_lambda_global(ctx, 0, ctx->sc.n, ctx->keys_sorted, ctx->table.p, ctx->pos[ctx->cur].p, pstar_in,
-                              pstar_out, rho_out);
+  const float4 *pos_mass = ctx->pos[ctx->cur].p;
+  if (ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS)
+    return launch_lambda_global(ctx, first, count, ctx->keys_sorted, ctx->table.p, pos_mass, pstar_in, pstar_out, rho_out);
+  return launch_lambda_list(ctx, first, count, ctx->keys_sorted, ctx->table.p, pos_mass, pstar_in, pstar_out, rho_out, role, want);
 }
-static int delta_pass(pbf_ctx *ctx, const float4 *pstar_in, float4 *pstar_out) {
+
+int solver_delta(pbf_ctx *ctx, uint32_t first, uint32_t count, const float4 *pstar_in, float4 *pstar_out, const uint32_t *role,
+                 uint32_t want) {
   PhaseScope ps(ctx, PBF_PH_DELTA);
-  if (!(ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS))
-    return launch_delta_list(ctx, 0, ctx->sc.n, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out);
-  return launch_delta_global(ctx, 0, ctx->sc.n, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out);
+  if (ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS)
+    return launch_delta_global(ctx, first, count, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out);
+  return launch_delta_list(ctx, first, count, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out, role, want);
 }
 
 static int validate(pbf_ctx *ctx, const pbf_params *p) {
@@ -189,8 +192,8 @@ static int step_device(pbf_ctx *ctx, const pbf_params &p) {
     PBF_TRY(launch_diffuse(ctx, ctx->keys_sorted, ctx->table.p, ctx->col[ctx->cur_col].p, ctx->col[ctx->cur_col ^ 1].p));
   ctx->cur_col ^= 1;
   for (uint64_t it = 0; it < p.iteration; ++it) {
-    PBF_TRY(lambda_pass(ctx, ctx->pstar[0].p, ctx->pstar[1].p, it + 1 == p.iteration ? ctx->rho.p : nullptr));
-    PBF_TRY(delta_pass(ctx, ctx->pstar[1].p, ctx->pstar[0].p));
+    PBF_TRY(solver_lambda(ctx, 0, n, ctx->pstar[0].p, ctx->pstar[1].p, it + 1 == p.iteration ? ctx->rho.p : nullptr));
+    PBF_TRY(solver_delta(ctx, 0, n, ctx->pstar[1].p, ctx->pstar[0].p));
   }
   PBF_TRY(launch_finalise(ctx, ctx->pstar[0].p, ctx->pos[ctx->cur].p, ctx->vel[ctx->cur].p));
   ctx->n_triangles = 0;
@@ -271,6 +274,7 @@ int pbf_create(pbf_ctx **out, float h, int device) {
     return PBF_ERR_CUDA;
   }
   ctx->own_stream = true;
+  if (const char *e = getenv("PBF_LIST_CAP")) ctx->list_cap = atoi(e) == 64 ? 64 : (int)kListMax;
   *out = ctx;
   return PBF_OK;
 }

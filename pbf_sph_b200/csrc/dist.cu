@@ -828,29 +828,20 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
       c->sc.n = d->n_local;
       float *rho = it + 1 == p.iteration ? c->rho.p : nullptr;
       const bool have_ghosts = d->n_glo + d->n_ghi != 0;
-      {
-        PhaseScope ps(c, PBF_PH_LAMBDA);
-        PBF_TRY(launch_lambda_list(c, 0, d->n_local, c->keys_sorted, c->table.p, c->pos[c->cur].p, c->pstar[0].p, c->pstar[1].p, rho,
-                                   have_ghosts ? d->role.p : nullptr, kRoleLambda));
-      }
+      PBF_TRY(solver_lambda(c, 0, d->n_local, c->pstar[0].p, c->pstar[1].p, rho, have_ghosts ? d->role.p : nullptr, kRoleLambda));
       if (d->n_own == 0) continue;
       if (exchange && d->n_send) {
         // boundary particles first; their halo goes out on the comm stream while the interior pass runs
-        {
-          PhaseScope ps(c, PBF_PH_DELTA);
-          PBF_TRY(launch_delta_list(c, d->own_off, d->n_own, c->keys_sorted, c->table.p, c->pstar[1].p, c->pstar[0].p, d->role.p, kRoleBoundary));
-        }
+        PBF_TRY(solver_delta(c, d->own_off, d->n_own, c->pstar[1].p, c->pstar[0].p, d->role.p, kRoleBoundary));
         PBF_CUDA(c, cudaEventRecord(d->ev_boundary, c->stream));
         PBF_CUDA(c, cudaStreamWaitEvent(d->comm_stream, d->ev_boundary, 0));
         pack_pstar_kernel<<<div_up(d->n_send, kBlk), kBlk, 0, d->comm_stream>>>(d->n_send, d->own_off, d->send_idx.p, c->pstar[0].p, d->sb_a.p);
         PBF_LAUNCH_CHECK(c);
-        {
-          PhaseScope ps(c, PBF_PH_DELTA);
-          PBF_TRY(launch_delta_list(c, d->own_off, d->n_own, c->keys_sorted, c->table.p, c->pstar[1].p, c->pstar[0].p, d->role.p, kRoleInterior));
-        }
+        PBF_TRY(solver_delta(c, d->own_off, d->n_own, c->pstar[1].p, c->pstar[0].p, d->role.p, kRoleInterior));
       } else {
-        PhaseScope ps(c, PBF_PH_DELTA);
-        PBF_TRY(launch_delta_list(c, d->own_off, d->n_own, c->keys_sorted, c->table.p, c->pstar[1].p, c->pstar[0].p, nullptr, 0));
+        // (role: ghosts are part of the local array; only owned particles move)
+        PBF_TRY(solver_delta(c, d->own_off, d->n_own, c->pstar[1].p, c->pstar[0].p, have_ghosts ? d->role.p : nullptr,
+                             kRoleBoundary | kRoleInterior));
         if (exchange) {  // a rank that sends nothing still takes part in the exchange
           PBF_CUDA(c, cudaEventRecord(d->ev_boundary, c->stream));
           PBF_CUDA(c, cudaStreamWaitEvent(d->comm_stream, d->ev_boundary, 0));

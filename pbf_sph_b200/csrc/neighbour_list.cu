@@ -1,19 +1,26 @@
 // neighbour_list.cu — the production form of the solver iteration (ompsph.hpp:215-249; 84 % of the reference's step).
 //
-// ncu on the plain one-pass kernels (neighbour.cu) shows an ISSUE-bound kernel (84 % issue-active) running at 16 of
-// 32 lanes: a particle has ~130-270 candidates in its 27 cells but only ~25-50 lie within h, every lane hits at
-// different candidates, so the expensive kernel-function code runs for almost every candidate at ~20 % utilisation.
-// Positions do not change between the lambda pass and the delta pass of one iteration, so the in-radius set is
-// found ONCE per iteration:
-//   lambda pass  phase 1: walk the 27 cells (18 contiguous runs, cells.cuh) and test every candidate — a 7-flop test,
-//                         nothing else — appending each hit's index to the particle's row of a neighbour list in
-//                         global memory (column layout nl[k][particle]: phase-2 reads are fully coalesced);
-//                phase 2: evaluate the density / gradient sums over the hits only, all lanes busy.
-//   delta pass   phase 2 only: no cell walk, no tests — reads the list the lambda pass left.
+// ncu on the plain one-pass kernels (neighbour.cu) shows an ISSUE-bound kernel running at 16 of 32 lanes: a particle
+// has ~130-270 candidates in its 27 cells but only ~25-50 lie within h, every lane hits at different candidates, so
+// the expensive kernel-function code runs for almost every candidate at ~20 % utilisation.  Positions do not change
+// between the lambda pass and the delta pass of one iteration, so the in-radius set is found ONCE per iteration:
+//
+//   lambda pass  phase 1  walk the 27 cells as 9 (y,z) rows of two contiguous runs each (an even-x cell and its +x
+//                         neighbour are consecutive Morton keys); the cell-table look-ups of row r+1 are issued
+//                         before row r is scanned.  Every candidate gets the 7-flop distance test and nothing else;
+//                         a hit appends the candidate's index to the particle's column of the list in global memory
+//                         (nl[k][particle]: lanes with equal k write one 128-byte line) with ONE predicated store
+//                         and a predicated 64-bit pointer bump — no divergent branch, no per-candidate bounds test.
+//                phase 2  density / gradient sums over the hits only.
+//   delta pass            no cell walk, no tests: reads the list the lambda pass left.
+//
+// (A shared-memory list — 2 instructions per append, indices for phase 2 from shared memory — was measured too: at
+// 256 B per thread it leaves 24 warps and 64 KB of L1 per SM, and the candidate gathers, which live on the L1 hit
+// rate, made the kernel 20 % slower than this form.)
+//
 // The list keeps the candidates in the reference's visiting order, so every sum is formed in the reference's
-// order (sph.hpp:215-236).  A particle with more than kListMax hits (particles piled into one cell) is flagged and
-// handled by the one-pass code in both passes.  The list costs ~3 x 4 B x hits of HBM/L2 traffic per particle and
-// iteration — about 0.4 GB per iteration at 1 M particles — in exchange for ~3x fewer issued instructions.
+// order (sph.hpp:215-236).  A particle with more than kCap hits (particles piled into one cell) is flagged and
+// handled by the one-pass code in both passes.
 #include "cells.cuh"
 #include "common.cuh"
 #include "pair_math.cuh"
@@ -24,22 +31,47 @@ namespace {
 
 constexpr int kBlock = 128;
 
-// Predicated 32-bit global store (one @p STG, no divergent branch).
+// Predicated 32-bit global store (one @p STG, no divergent branch: with ~1 hit in 5 candidates some lane would take
+// a branch for most candidates anyway).  Streaming (.cs): the list is written once and read once per pass; it must not
+// push the 16 B/particle pStar array — which every candidate test gathers from — out of L2.
 __device__ __forceinline__ void store_if(uint32_t *p, uint32_t v, bool pred) {
   asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.b32 [%0], %1;\n\t}" ::"l"(p), "r"(v),
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.b32 [%0], %1;\n\t}" ::"l"(p), "r"(v),
       "r"((uint32_t)pred)
       : "memory");
 }
 
-template <bool kStrict>
+// cell-table bounds of one (y,z) row of the 27-cell neighbourhood: the merged pair run and the single cell
+struct RowRuns {
+  uint32_t ps, pe, ss, se;
+};
+
+__device__ __forceinline__ RowRuns load_row(const uint32_t *__restrict__ table, uint32_t G, uint32_t myz, uint32_t pair_lo,
+                                            uint32_t single) {
+  RowRuns r;
+  const uint32_t op = myz | pair_lo, os = myz | single;
+  if (op + 2u < G) {  // both cells of the pair, and the entry after them, exist
+    r.ps = __ldg(table + op);
+    r.pe = __ldg(table + op + 2);
+  } else {            // at the end of the table fall back to the per-cell rule (cell G-1 is empty, sph.hpp:203-213)
+    uint32_t s2, e2;
+    cell_range(table, G, op, r.ps, r.pe);
+    cell_range(table, G, op + 1u, s2, e2);
+    if (r.pe == r.ps) { r.ps = s2; r.pe = e2; } else if (e2 != s2) r.pe = e2;  // adjacent when both non-empty
+  }
+  cell_range(table, G, os, r.ss, r.se);
+  return r;
+}
+
+template <bool kStrict, int kCap>
 __global__ void __launch_bounds__(kBlock) lambda_list_kernel(StepConst c, uint32_t first, uint32_t count,
                                                              const uint32_t *__restrict__ keys,
                                                              const uint32_t *__restrict__ table,
                                                              const float4 *__restrict__ pos_mass,
                                                              const float4 *__restrict__ pstar_in,
                                                              float4 *__restrict__ pstar_out, float *__restrict__ rho_out,
-                                                             uint32_t *nl, uint32_t stride, uint32_t *__restrict__ n_hits,
+                                                             uint32_t *nl, uint32_t stride, uint32_t inv_stride,
+                                                             uint32_t *__restrict__ n_hits,
                                                              const uint32_t *__restrict__ role, uint32_t want) {
   const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
   if (t >= count) return;
@@ -48,28 +80,63 @@ __global__ void __launch_bounds__(kBlock) lambda_list_kernel(StepConst c, uint32
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t key = __ldg(keys + a);
   const float mass = __ldg(&pos_mass[a].w);
+
   // ---- phase 1: find the hits
-  // The append is written so that it compiles to a predicated store plus a predicated increment (no divergent
-  // branch): with ~1 hit in 5 candidates a branch would be taken by some lane for most candidates anyway.
-  uint32_t k = 0;
-  uint32_t slot = a;  // index of nl[k * stride + a]; fits 32 bits (checked by the launcher)
-  for_each_run(key, c.G, table, [&](uint32_t s, uint32_t e) {
+  const uint32_t kx = key & kAxisMask, ky = (key >> 1) & kAxisMask, kz = (key >> 2) & kAxisMask;
+  const uint32_t xm = dilated_dec(kx), xp = dilated_inc(kx);
+  const bool x_even = (kx & 1u) == 0u;        // even: (x, x+1) are consecutive keys; odd: (x-1, x) are
+  const uint32_t pair_lo = x_even ? kx : xm;  // first cell of the merged pair
+  const uint32_t single = x_even ? xm : xp;
+  const uint32_t ym = dilated_dec(ky) << 1, y0 = ky << 1, yp = dilated_inc(ky) << 1;
+  const uint32_t zm = dilated_dec(kz) << 2, z0 = kz << 2, zp = dilated_inc(kz) << 2;
+  auto row_key = [&](int r) {
+    const int iz = r / 3, iy = r - 3 * iz;
+    return (iz == 0 ? zm : (iz == 1 ? z0 : zp)) | (iy == 0 ? ym : (iy == 1 ? y0 : yp));
+  };
+  uint32_t slot = a;  // element index of the next free entry: hit k lives at nl[k * stride + a]
+  uint32_t over = 0;  // hits that did not fit
+  auto scan_run = [&](uint32_t s, uint32_t e) {
+    // hits so far, exactly: (slot - a) is a small multiple of stride, inv_stride = ceil(2^32 / stride)
+    uint32_t k = __umulhi(slot - a, inv_stride);
+    if (k + (e - s) <= (uint32_t)kCap) {  // cannot overflow: no per-candidate capacity test, no hit counter
 #pragma unroll 4
-    for (uint32_t b = s; b < e; ++b) {
-      const bool hit = LambdaAcc<kStrict>::test(c, pa, ldg4(pstar_in + b));
-      store_if(nl + slot, b, hit && k < kListMax);
-      if (hit) { ++k; slot += stride; }
+      for (uint32_t b = s; b < e; ++b) {
+        const bool hit = LambdaAcc<kStrict>::test(c, pa, ldg4(pstar_in + b));
+        store_if(nl + slot, b, hit);
+        slot += hit ? stride : 0u;
+      }
+    } else {
+#pragma unroll 1
+      for (uint32_t b = s; b < e; ++b) {
+        const bool hit = LambdaAcc<kStrict>::test(c, pa, ldg4(pstar_in + b));
+        const bool fits = hit && k < (uint32_t)kCap;
+        store_if(nl + slot, b, fits);
+        slot += fits ? stride : 0u;
+        k += fits ? 1u : 0u;
+        over += (hit && !fits) ? 1u : 0u;
+      }
     }
-  });
+  };
+  RowRuns nxt = load_row(table, c.G, row_key(0), pair_lo, single);
+#pragma unroll 1
+  for (int r = 0; r < 9; ++r) {
+    const RowRuns cur = nxt;
+    if (r < 8) nxt = load_row(table, c.G, row_key(r + 1), pair_lo, single);
+    // order along x is (x-1, x, x+1): the single cell comes first when x is even, last when x is odd
+    scan_run(x_even ? cur.ss : cur.ps, x_even ? cur.se : cur.pe);
+    scan_run(x_even ? cur.ps : cur.ss, x_even ? cur.pe : cur.se);
+  }
+  const uint32_t k = __umulhi(slot - a, inv_stride) + over;
   n_hits[a] = k;
-  // ---- phase 2: the sums
+
+  // ---- phase 2: the sums over the hits
   LambdaAcc<kStrict> acc;
   acc.init();
   acc.set_mass(mass);
-  if (k <= kListMax) {
+  if (k <= (uint32_t)kCap) {
     const uint32_t *row = nl + a;
 #pragma unroll 4
-    for (uint32_t i = 0; i < k; ++i, row += stride) acc.add_in(c, pa, ldg4(pstar_in + __ldcg(row)));
+    for (uint32_t i = 0; i < k; ++i, row += stride) acc.add_in(c, pa, ldg4(pstar_in + __ldcs(row)));
   } else {
     for_each_candidate(key, c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
@@ -79,7 +146,7 @@ __global__ void __launch_bounds__(kBlock) lambda_list_kernel(StepConst c, uint32
   if (rho_out) rho_out[a] = rho;
 }
 
-template <bool kStrict>
+template <bool kStrict, int kCap>
 __global__ void __launch_bounds__(kBlock) delta_list_kernel(StepConst c, uint32_t first, uint32_t count,
                                                             const uint32_t *__restrict__ keys,
                                                             const uint32_t *__restrict__ table,
@@ -91,21 +158,52 @@ __global__ void __launch_bounds__(kBlock) delta_list_kernel(StepConst c, uint32_
   const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
   if (t >= count) return;
   const uint32_t a = first + t;
-  if (role && !(__ldg(role + a) & want)) return;  // multi-GPU: not this pass's particle (dist.cu roles)
+  if (role && !(__ldg(role + a) & want)) return;
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t k = __ldg(n_hits + a);
   DeltaAcc<kStrict> acc;
   acc.init();
-  if (k <= kListMax) {
+  if (k <= (uint32_t)kCap) {
     const uint32_t *row = nl + a;
-#pragma unroll 4
+#pragma unroll 8
     for (uint32_t i = 0; i < k; ++i, row += stride) {
-      acc.add_in(c, pa, ldg4(pstar_in + __ldg(row)));  // add_in skips the particle itself (r < EPSILON)
+      acc.add_in(c, pa, ldg4(pstar_in + __ldcs(row)));  // add_in skips the particle itself (r < EPSILON)
     }
   } else {
     for_each_candidate(__ldg(keys + a), c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
   pstar_out[a] = acc.finish(c, pa);
+}
+
+template <int kCap> int launch_lambda_cap(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
+                                          const uint32_t *table, const float4 *pos_mass, const float4 *pstar_in,
+                                          float4 *pstar_out, float *rho_out, uint32_t stride, const uint32_t *role,
+                                          uint32_t want) {
+  uint32_t *nl4 = ctx->nl.p;
+  if (ctx->flags & PBF_FLAG_STRICT_FP)
+    lambda_list_kernel<true, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
+        ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride,
+        (uint32_t)(((1ull << 32) + stride - 1) / stride), ctx->nl_count.p, role, want);
+  else
+    lambda_list_kernel<false, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
+        ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride,
+        (uint32_t)(((1ull << 32) + stride - 1) / stride), ctx->nl_count.p, role, want);
+  PBF_LAUNCH_CHECK(ctx);
+  return PBF_OK;
+}
+
+template <int kCap> int launch_delta_cap(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
+                                         const uint32_t *table, const float4 *pstar_in, float4 *pstar_out,
+                                         const uint32_t *role, uint32_t want) {
+  const uint32_t *nl4 = ctx->nl.p;
+  if (ctx->flags & PBF_FLAG_STRICT_FP)
+    delta_list_kernel<true, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
+        ctx->sc, first, count, keys_sorted, table, pstar_in, pstar_out, nl4, ctx->nl_stride, ctx->nl_count.p, role, want);
+  else
+    delta_list_kernel<false, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
+        ctx->sc, first, count, keys_sorted, table, pstar_in, pstar_out, nl4, ctx->nl_stride, ctx->nl_count.p, role, want);
+  PBF_LAUNCH_CHECK(ctx);
+  return PBF_OK;
 }
 
 }  // namespace
@@ -117,35 +215,21 @@ int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint3
   const uint32_t n = ctx->sc.n;
   const uint32_t stride = (n + 31u) & ~31u;  // rows start on 128-byte boundaries
   if ((uint64_t)stride * (kListMax + 1) >= (1ull << 32))
-    return fail(ctx, PBF_ERR_INVALID, "n", "more than 2^32 / 65 particles on one device (neighbour-list indexing)");
+    return fail(ctx, PBF_ERR_INVALID, "n", "too many particles on one device (neighbour-list indexing)");
   PBF_CUDA(ctx, ctx->nl.reserve((size_t)stride * kListMax));
   PBF_CUDA(ctx, ctx->nl_count.reserve(n));
   ctx->nl_stride = stride;
-  if (ctx->flags & PBF_FLAG_STRICT_FP)
-    lambda_list_kernel<true><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, ctx->nl.p, stride, ctx->nl_count.p,
-        role, want);
-  else
-    lambda_list_kernel<false><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, ctx->nl.p, stride, ctx->nl_count.p,
-        role, want);
-  PBF_LAUNCH_CHECK(ctx);
-  return PBF_OK;
+  if (ctx->list_cap == 64)
+    return launch_lambda_cap<64>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
+  return launch_lambda_cap<kListMax>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
 }
 
 int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                       const float4 *pstar_in, float4 *pstar_out, const uint32_t *role, uint32_t want) {
   if (count == 0) return PBF_OK;
-  if (ctx->flags & PBF_FLAG_STRICT_FP)
-    delta_list_kernel<true><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, first, count, keys_sorted, table, pstar_in, pstar_out, ctx->nl.p, ctx->nl_stride, ctx->nl_count.p,
-        role, want);
-  else
-    delta_list_kernel<false><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, first, count, keys_sorted, table, pstar_in, pstar_out, ctx->nl.p, ctx->nl_stride, ctx->nl_count.p,
-        role, want);
-  PBF_LAUNCH_CHECK(ctx);
-  return PBF_OK;
+  if (ctx->list_cap == 64)
+    return launch_delta_cap<64>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
+  return launch_delta_cap<kListMax>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
 }
 
 }  // namespace pbf
