@@ -179,6 +179,15 @@ struct pbf_ctx {
   pbf::DevBuf<uint32_t> nl, nl_count;
   uint32_t nl_stride = 0;
   int list_cap = 96;  // hits kept per particle in the neighbour list (kListMax, or 64 via PBF_LIST_CAP for A/B runs)
+  // per-step plan of the warp-per-cell search (cell_search.cu): cells to search, their targets and flat candidate lists
+  pbf::DevBuf<uint32_t> plan_heads, plan_cand;
+  pbf::DevBuf<uint4> plan_info;
+  bool plan_valid = false;  // cleared whenever the cell table is rebuilt
+  uint32_t plan_first = 0, plan_count = 0, plan_want = 0;
+  const uint32_t *plan_role = nullptr;
+  // 0: thread-per-particle search walking the cell table (neighbour_list.cu, the production form);
+  // 1: warp-per-cell search over the per-step plan (cell_search.cu, PBF_SEARCH=cells).  Both write the same lists.
+  int search_mode = 0;
 
   pbf_grid_info grid{};
   pbf::StepConst sc{};
@@ -257,6 +266,12 @@ constexpr uint32_t kListMax = 96;  // hits stored per particle; beyond that the 
 int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                        const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
                        const uint32_t *role = nullptr, uint32_t want = 0);
+// per-step search plan (cell_search.cu): ctx->plan_* for the cells of [first, first + count) whose role matches
+int ensure_search_plan(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
+                       const uint32_t *role, uint32_t want);
+// warp-per-cell neighbour search (cell_search.cu): fills ctx->nl / ctx->nl_count for the matching particles
+int launch_search_cells(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
+                        const float4 *pstar_in, uint32_t stride, const uint32_t *role, uint32_t want);
 // role != nullptr: particle a is processed only when role[a] & want (multi-GPU: ring-1 / boundary / interior, dist.cu)
 int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                       const float4 *pstar_in, float4 *pstar_out, const uint32_t *role = nullptr, uint32_t want = 0);

@@ -275,6 +275,7 @@ int pbf_create(pbf_ctx **out, float h, int device) {
   }
   ctx->own_stream = true;
   if (const char *e = getenv("PBF_LIST_CAP")) ctx->list_cap = atoi(e) == 64 ? 64 : (int)kListMax;
+  if (const char *e = getenv("PBF_SEARCH")) ctx->search_mode = (e[0] == 'c') ? 1 : 0;
   *out = ctx;
   return PBF_OK;
 }
@@ -293,6 +294,7 @@ void pbf_destroy(pbf_ctx *ctx) {
   ctx->mc_pn.release(); ctx->mc_c.release(); ctx->mc_count.release(); ctx->mc_offset.release();
   ctx->mesh_vs.release(); ctx->mesh_ns.release(); ctx->mesh_cs.release();
   ctx->blk_list.release(); ctx->blk_info.release(); ctx->nl.release(); ctx->nl_count.release();
+  ctx->plan_heads.release(); ctx->plan_cand.release(); ctx->plan_info.release();
   if (ctx->flag_dev) cudaFree(ctx->flag_dev);
   if (ctx->flag_host) cudaFreeHost(ctx->flag_host);
   if (ctx->mc_total_dev) cudaFree(ctx->mc_total_dev);

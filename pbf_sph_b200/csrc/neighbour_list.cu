@@ -29,7 +29,13 @@ namespace pbf {
 
 namespace {
 
-constexpr int kBlock = 128;
+#ifndef PBF_NL_BLOCK
+#define PBF_NL_BLOCK 128
+#endif
+#ifndef PBF_NL_MINB
+#define PBF_NL_MINB 1
+#endif
+constexpr int kBlock = PBF_NL_BLOCK;
 
 // Predicated 32-bit global store (one @p STG, no divergent branch: with ~1 hit in 5 candidates some lane would take
 // a branch for most candidates anyway).  Streaming (.cs): the list is written once and read once per pass; it must not
@@ -64,7 +70,7 @@ __device__ __forceinline__ RowRuns load_row(const uint32_t *__restrict__ table, 
 }
 
 template <bool kStrict, int kCap>
-__global__ void __launch_bounds__(kBlock) lambda_list_kernel(StepConst c, uint32_t first, uint32_t count,
+__global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepConst c, uint32_t first, uint32_t count,
                                                              const uint32_t *__restrict__ keys,
                                                              const uint32_t *__restrict__ table,
                                                              const float4 *__restrict__ pos_mass,
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(kBlock) lambda_list_kernel(StepConst c, uint32
 }
 
 template <bool kStrict, int kCap>
-__global__ void __launch_bounds__(kBlock) delta_list_kernel(StepConst c, uint32_t first, uint32_t count,
+__global__ void __launch_bounds__(kBlock, PBF_NL_MINB) delta_list_kernel(StepConst c, uint32_t first, uint32_t count,
                                                             const uint32_t *__restrict__ keys,
                                                             const uint32_t *__restrict__ table,
                                                             const float4 *__restrict__ pstar_in,
@@ -175,11 +181,59 @@ __global__ void __launch_bounds__(kBlock) delta_list_kernel(StepConst c, uint32_
   pstar_out[a] = acc.finish(c, pa);
 }
 
+// Phase 2 alone, for lists written by the warp-per-cell search (cell_search.cu): the density / gradient sums over
+// the hits, in list (= the reference's visiting) order.
+template <bool kStrict, int kCap>
+__global__ void __launch_bounds__(kBlock) lambda_sums_kernel(StepConst c, uint32_t first, uint32_t count,
+                                                             const uint32_t *__restrict__ keys,
+                                                             const uint32_t *__restrict__ table,
+                                                             const float4 *__restrict__ pos_mass,
+                                                             const float4 *__restrict__ pstar_in,
+                                                             float4 *__restrict__ pstar_out, float *__restrict__ rho_out,
+                                                             const uint32_t *__restrict__ nl, uint32_t stride,
+                                                             const uint32_t *__restrict__ n_hits,
+                                                             const uint32_t *__restrict__ role, uint32_t want) {
+  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
+  if (t >= count) return;
+  const uint32_t a = first + t;
+  if (role && !(__ldg(role + a) & want)) return;
+  const float4 pa = ldg4(pstar_in + a);
+  const float mass = __ldg(&pos_mass[a].w);
+  const uint32_t k = __ldg(n_hits + a);
+  LambdaAcc<kStrict> acc;
+  acc.init();
+  acc.set_mass(mass);
+  if (k <= (uint32_t)kCap) {
+    const uint32_t *row = nl + a;
+#pragma unroll 4
+    for (uint32_t i = 0; i < k; ++i, row += stride) acc.add_in(c, pa, ldg4(pstar_in + __ldcs(row)));
+  } else {
+    for_each_candidate(__ldg(keys + a), c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
+  }
+  float rho;
+  const float lambda = acc.finish(c, mass, rho);
+  pstar_out[a] = make_float4(pa.x, pa.y, pa.z, lambda);
+  if (rho_out) rho_out[a] = rho;
+}
+
 template <int kCap> int launch_lambda_cap(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
                                           const uint32_t *table, const float4 *pos_mass, const float4 *pstar_in,
                                           float4 *pstar_out, float *rho_out, uint32_t stride, const uint32_t *role,
                                           uint32_t want) {
   uint32_t *nl4 = ctx->nl.p;
+  if (ctx->search_mode == 1) {  // warp-per-cell search (PBF_SEARCH=cells), then the sums over its lists
+    PBF_TRY(launch_search_cells(ctx, first, count, keys_sorted, table, pstar_in, stride, role, want));
+    if (ctx->flags & PBF_FLAG_STRICT_FP)
+      lambda_sums_kernel<true, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
+          ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, ctx->nl_count.p,
+          role, want);
+    else
+      lambda_sums_kernel<false, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
+          ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, ctx->nl_count.p,
+          role, want);
+    PBF_LAUNCH_CHECK(ctx);
+    return PBF_OK;
+  }
   if (ctx->flags & PBF_FLAG_STRICT_FP)
     lambda_list_kernel<true, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
         ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride,
@@ -216,7 +270,7 @@ int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint3
   const uint32_t stride = (n + 31u) & ~31u;  // rows start on 128-byte boundaries
   if ((uint64_t)stride * (kListMax + 1) >= (1ull << 32))
     return fail(ctx, PBF_ERR_INVALID, "n", "too many particles on one device (neighbour-list indexing)");
-  PBF_CUDA(ctx, ctx->nl.reserve((size_t)stride * kListMax));
+  PBF_CUDA(ctx, ctx->nl.reserve((size_t)stride * (kListMax + 1)));  // + the dump row of cell_search.cu
   PBF_CUDA(ctx, ctx->nl_count.reserve(n));
   ctx->nl_stride = stride;
   if (ctx->list_cap == 64)

@@ -21,6 +21,35 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
   return y;
 }
 
+// ---- packed pairs of floats (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE single operations per instruction) -----------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 __device__ __forceinline__ float strict_distance(const float4 a, const float4 b) {
   const float dx = fsub(b.x, a.x), dy = fsub(b.y, a.y), dz = fsub(b.z, a.z);  // glm::distance = length(b - a)
   return fsqrt(fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));          // dot = (x*x + y*y) + z*z

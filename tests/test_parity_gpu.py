@@ -162,6 +162,28 @@ def test_dense_cell_collision(gpu, oracle_mod):
     assert np.array_equal(gpu_xs["id"], cpu["id"])
 
 
+@pytest.mark.parametrize("flags", [0, FLAG_STRICT_FP])
+def test_warp_per_cell_search_is_bit_identical(gpu, oracle_mod, warm_s0, monkeypatch, flags):
+    """PBF_SEARCH=cells (cell_search.cu: one warp per occupied cell, packed FADD2/FFMA2 tests, staged lists) must write
+    the very lists the production thread-per-particle search writes: identical lambda, positions and velocities —
+    on the warm stock scene, on out-of-grid particles and on a cell with thousands of particles (list overflow)."""
+    p, snap = warm_s0
+    cases = [(scenes.apply_motion(p, 40), snap)]
+    pq, xs = scenes.two_cubes(20000, 2)
+    xs = xs[:6000].copy()
+    xs["position"][:3000] = (0.0, 1000.0, 0.0)
+    xs["position"][:3000] += np.random.default_rng(3).uniform(0, 5, (3000, 3)).astype(np.float32)
+    xs["velocity"][3000:3064] = 55.0  # and some that leave the grid
+    cases.append((pq, xs))
+    for params, start in cases:
+        monkeypatch.delenv("PBF_SEARCH", raising=False)
+        ref, t_ref, _ = run_gpu(params, start, flags)
+        monkeypatch.setenv("PBF_SEARCH", "cells")
+        alt, t_alt, _ = run_gpu(params, start, flags)
+        assert np.array_equal(t_alt["lambda"], t_ref["lambda"], equal_nan=True)
+        assert alt.tobytes() == ref.tobytes()
+
+
 def test_obstacle_rejected(gpu):
     p, xs = scenes.two_cubes(2000, 2)
     xs["type"][5] = 1
