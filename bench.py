@@ -57,18 +57,64 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md 'clocks' line)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md 'clocks' line): an NVML polling thread
+    (20 ms period, started before the region, stopped after it); `nvidia-smi -lms` as the fallback when NVML cannot
+    be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop, self.how = index, [], None, threading.Event(), None
+
+    def _nvml_loop(self, nv, h, mx):
+        bits = [getattr(nv, n, 0) for n in ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksEventReasonHwThermalSlowdown",
+                                            "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksEventReasonSwPowerCap")]
+        alt = [getattr(nv, n, 0) for n in ("nvmlClocksThrottleReasonHwSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown",
+                                           "nvmlClocksThrottleReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwPowerCap")]
+        bits = [b or a for b, a in zip(bits, alt)]
+        while True:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if (b and r & b) else "Not Active" for b in bits])
+            except Exception:
+                pass
+            if self.stop.wait(0.02):
+                break
 
     def __enter__(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: go through the PCI bus id of the CUDA device
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(nv.nvmlDeviceGetCount()):
+                    hi = nv.nvmlDeviceGetHandleByIndex(i)
+                    if int(nv.nvmlDeviceGetPciInfo(hi).bus) == int(bus):
+                        h = hi
+                        break
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.how = "nvml"
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h, mx), daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            pass
+        try:
+            self.how = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -81,6 +127,7 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -88,20 +135,21 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        elif getattr(self, "t", None):
+            self.t.join(timeout=1)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in list(self.rows):
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
                 continue
-            for name, v in zip(names, r[2:6]):
+            for name, v in zip(self.NAMES, r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.how}
 
 
 def workload(name: str, world: int):
@@ -187,6 +235,37 @@ def run_reference(args):
     }))
 
 
+def roofline_of(prof, n, iters, steps):
+    """Roofline object of the dominant kernel family: algorithmic bytes per launch (ALG_BYTES x particles the launch
+    processes) / the family's average launch duration from the library's CUDA events on its own stream, against the
+    measured HBM copy peak.  `traffic` = DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
+    of the same workload (profiles/ncu_traffic.json), or null when the family has no capture."""
+    peak, peak_src = peaks()
+    fam = max(("lambda", "delta"), key=lambda k: prof["ms"][k])
+    n_launch = max(1, prof["launches"][fam])
+    avg_ms = prof["ms"][fam] / n_launch
+    achieved = n * ALG_BYTES[fam] / (avg_ms * 1e-3) / 1e9
+    breakdown = {k: round(v / steps, 4) for k, v in prof["ms"].items() if v > 0}
+    per_kernel = {}
+    for k, b in ALG_BYTES.items():
+        if prof["launches"].get(k) and prof["ms"][k] > 0:
+            per_kernel[k] = round(n * b / (prof["ms"][k] / prof["launches"][k] * 1e-3) / 1e9, 1) if k in ("lambda", "delta") \
+                else round(n * b / (prof["ms"][k] / steps * 1e-3) / 1e9, 1)
+    traffic, traffic_src = None, None
+    tf = ROOT / "profiles" / "ncu_traffic.json"
+    if tf.exists():
+        t = json.loads(tf.read_text())
+        if fam in t.get("dram_bytes_per_launch", {}) and t.get("particles") == n:
+            traffic, traffic_src = t["dram_bytes_per_launch"][fam], t.get("source")
+    return {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "bytes_per_particle": ALG_BYTES[fam], "avg_launch_ms": avg_ms,
+            "note": "the neighbour passes are bound by the L1 data pipe and instruction issue (~170 candidate pairs per "
+                    "particle, one 16-byte position through L1 per pair and lane), not by HBM; see DESIGN.md §4 and "
+                    "profiles/r01c_search_experiments.txt", "ms_per_step_by_family": breakdown,
+            "achieved_GBps_by_family": per_kernel}
+
+
 # ------------------------------------------------------------------------------------------------ our arm, 1 GPU
 def run_single(args):
     import torch
@@ -221,23 +300,7 @@ def run_single(args):
     prof = s.profile()
     value = n * iters * args.steps / (ms_total * 1e-3)
 
-    # roofline of the dominant kernel family
-    peak, peak_src = peaks()
-    fam = max(("lambda", "delta"), key=lambda k: prof["ms"][k])
-    n_launch = max(1, prof["launches"][fam])
-    avg_ms = prof["ms"][fam] / n_launch
-    achieved = n * ALG_BYTES[fam] / (avg_ms * 1e-3) / 1e9
-    breakdown = {k: round(v / args.steps, 4) for k, v in prof["ms"].items() if v > 0}
-    per_kernel = {}
-    for k, b in ALG_BYTES.items():
-        if prof["launches"].get(k) and prof["ms"][k] > 0:
-            calls = args.steps * (iters if k in ("lambda", "delta") else 1)
-            per_kernel[k] = round(n * b / (prof["ms"][k] / calls * 1e-3) / 1e9, 1)
-    roofline = {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "bytes_per_particle": ALG_BYTES[fam], "avg_launch_ms": avg_ms,
-                "note": "neighbour passes are FP32/issue-bound (~130-270 candidate pairs per particle), not HBM-bound; "
-                        "see DESIGN.md §4", "ms_per_step_by_family": breakdown, "achieved_GBps_by_family": per_kernel}
+    roofline = roofline_of(prof, n, iters, args.steps)
 
     # end to end through the drop-in call, pinned host buffers
     snap = s.download()
@@ -304,7 +367,7 @@ def run_single(args):
 
 def run_multi(args):
     from pbf_sph_b200 import dist
-    dist.bench_main(args, workload, ClockSampler, METRIC, UNIT)
+    dist.bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of)
 
 
 def _protect_stdout():

@@ -143,6 +143,8 @@ struct pbf_ctx {
   uint32_t flags = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t side_stream = nullptr;  // colour diffusion runs here, beside the solver iterations
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;

@@ -186,15 +186,28 @@ static int step_device(pbf_ctx *ctx, const pbf_params &p) {
                                     ctx->nbr_count.p));
   }
   PBF_CUDA(ctx, ctx->col[ctx->cur_col ^ 1].reserve(n));
-  if (tiled)
-    PBF_TRY(launch_diffuse_tiled(ctx, ctx->keys_sorted, ctx->table.p, ctx->col[ctx->cur_col].p, ctx->col[ctx->cur_col ^ 1].p));
-  else
-    PBF_TRY(launch_diffuse(ctx, ctx->keys_sorted, ctx->table.p, ctx->col[ctx->cur_col].p, ctx->col[ctx->cur_col ^ 1].p));
+  // Colour diffusion feeds nothing inside the step (ompsph.hpp:189-206 touches colours only): it runs on a side stream
+  // beside the solver iterations — a shared-memory, latency-bound kernel under L1/issue-bound ones — and joins before
+  // finalise, i.e. before anything can read the colours.
+  {
+    PBF_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    PBF_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->side_stream;
+    const int rc = tiled ? launch_diffuse_tiled(ctx, ctx->keys_sorted, ctx->table.p, ctx->col[ctx->cur_col].p,
+                                                ctx->col[ctx->cur_col ^ 1].p)
+                         : launch_diffuse(ctx, ctx->keys_sorted, ctx->table.p, ctx->col[ctx->cur_col].p,
+                                          ctx->col[ctx->cur_col ^ 1].p);
+    ctx->stream = main_stream;
+    PBF_TRY(rc);
+    PBF_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  }
   ctx->cur_col ^= 1;
   for (uint64_t it = 0; it < p.iteration; ++it) {
     PBF_TRY(solver_lambda(ctx, 0, n, ctx->pstar[0].p, ctx->pstar[1].p, it + 1 == p.iteration ? ctx->rho.p : nullptr));
     PBF_TRY(solver_delta(ctx, 0, n, ctx->pstar[1].p, ctx->pstar[0].p));
   }
+  PBF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   PBF_TRY(launch_finalise(ctx, ctx->pstar[0].p, ctx->pos[ctx->cur].p, ctx->vel[ctx->cur].p));
   ctx->n_triangles = 0;
   ctx->mc_valid = false;
@@ -264,6 +277,9 @@ int pbf_create(pbf_ctx **out, float h, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->flag_dev, 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaHostAlloc(&ctx->flag_host, 4 * sizeof(int), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->mc_total_dev, 4 * sizeof(uint32_t));
@@ -301,6 +317,9 @@ void pbf_destroy(pbf_ctx *ctx) {
   if (ctx->mc_total_host) cudaFreeHost(ctx->mc_total_host);
   if (ctx->ev_created) for (int i = 0; i < pbf_ctx::kMaxEv; ++i) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
 }
 

@@ -121,7 +121,7 @@ class LocalGroup:
 
 
 # ------------------------------------------------------------------------------------------------- bench.py, N > 1
-def bench_main(args, workload, ClockSampler, METRIC, UNIT) -> None:
+def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> None:
     """One rank per GPU under torchrun: weak scaling (the dam-break block grows so that every GPU holds ~1 M
     particles), device time by CUDA events, max over ranks, rank 0 prints the JSON line."""
     import torch
@@ -215,7 +215,9 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT) -> None:
                        "settle_steps": args.settle, "decomposition": "Z-curve slabs, NCCL send/recv halo per solver iteration",
                        "l2": "no flush: the per-step working set exceeds the 126 MB L2"},
             "particle_steps_per_sec": n_total * args.steps / (ms_total * 1e-3),
-            "roofline": None, "cpu_baseline": None,
+            # rank 0's dominant kernel family over the particles rank 0 processes (owned + ghosts)
+            "roofline": roofline_of(prof, st["owned"] + st["ghosts"], iters, args.steps) if roofline_of else None,
+            "cpu_baseline": None,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(per_step_bytes),
                     "d2h_bytes_per_step": int(per_step_bytes), "steps": e2e_steps,
                     "api": "pbf_dist_upload (host AoS) -> pbf_dist_step -> pbf_dist_download, every step, all ranks"},
