@@ -7,8 +7,9 @@
 //   * empty xs: prints "Particles depleted", sleeps 5 ms, returns an empty Result (ompsph.hpp:122-126);
 //   * failures surface as std::runtime_error, which the drivers catch and rethrow (benchmark.cpp:34-37);
 //   * may be called from any thread, serially (visualise.cpp:85-109): the C ABI sets the device on every entry.
-// Sources and drains are the reference's host-side list edits (ompsph.hpp:91-120) and are reproduced here; wells and
-// queries are not part of the accelerated path (both drivers pass an empty Scene) and are rejected.
+// The whole sph::Scene is honoured on the device (scene.cu): sources emit and drains remove on the resident arrays
+// (ompsph.hpp:91-120), wells pull inside the prediction (:141-148), queries are answered from the step's cell table
+// (:167-186).
 #pragma once
 
 #include <algorithm>
@@ -66,46 +67,53 @@ public:
 
   sph::Result<T, N, V> advance(const sph::SphParams<T, N, V> &config, const sph::Scene<T, N, V> &scene,
                                std::vector<P> &xs) override {
-    if (!scene.wells.empty() || !scene.queries.empty())
-      throw std::runtime_error("sph::cuda_impl::Solver: wells and queries are not supported by the CUDA backend");
-    // sources: a floor(sqrt(rate)) x ceil(sqrt(rate)) sheet of new particles, spacing h*scale/2, centred on the source
-    const N spacing = h * config.scale / 2;
-    for (const auto &src : scene.sources) {
-      const N side = std::sqrt(static_cast<N>(src.rate));
-      const size_t width = size_t(std::floor(side)), depth = size_t(std::ceil(side));
-      for (size_t x = 0; x < width; ++x)
-        for (size_t z = 0; z < depth; ++z)
-          xs.emplace_back(src.tag, sph::Type::Fluid, N(1), src.colour,
-                          V<3, N>(src.centre.x - N(width) * N(0.5) * spacing + N(x) * spacing, src.centre.y,
-                                  src.centre.z - N(depth) * N(0.5) * spacing + N(z) * spacing),
-                          src.velocity);
+    // sph::Scene -> pbf_scene (plain arrays; the library copies them)
+    std::vector<pbf_well> wells;
+    std::vector<pbf_source> sources;
+    std::vector<pbf_drain> drains;
+    std::vector<pbf_query> queries;
+    for (const auto &w : scene.wells) wells.push_back({uint64_t(w.tag), {w.centre.x, w.centre.y, w.centre.z}, w.force});
+    for (const auto &s : scene.sources)
+      sources.push_back({uint64_t(s.tag), {s.centre.x, s.centre.y, s.centre.z}, {s.velocity.x, s.velocity.y, s.velocity.z},
+                         {s.colour.x, s.colour.y, s.colour.z, s.colour.w}, s.rate});
+    for (const auto &d : scene.drains) drains.push_back({uint64_t(d.tag), {d.centre.x, d.centre.y, d.centre.z}, d.width, d.depth});
+    for (const auto &q : scene.queries) queries.push_back({uint64_t(q.id), {q.point.x, q.point.y, q.point.z}});
+    const pbf_scene sc{wells.data(),  uint32_t(wells.size()),  sources.data(), uint32_t(sources.size()),
+                       drains.data(), uint32_t(drains.size()), queries.data(), uint32_t(queries.size())};
+    // sources append a floor(sqrt(rate)) x ceil(sqrt(rate)) sheet each (ompsph.hpp:93-104): make room for them
+    size_t emitted = 0;
+    for (const auto &s : scene.sources) {
+      const N side = std::sqrt(static_cast<N>(s.rate));
+      emitted += size_t(std::floor(side)) * size_t(std::ceil(side));
     }
-    // drains: fluid particles within `width` of a drain centre disappear
-    if (!scene.drains.empty())
-      xs.erase(std::remove_if(xs.begin(), xs.end(),
-                              [&](const P &p) {
-                                if (p.type == sph::Type::Obstacle) return false;
-                                for (const auto &d : scene.drains) {
-                                  const N dx = d.centre.x - p.position.x, dy = d.centre.y - p.position.y, dz = d.centre.z - p.position.z;
-                                  if (std::sqrt(dx * dx + dy * dy + dz * dz) < d.width) return true;
-                                }
-                                return false;
-                              }),
-               xs.end());
+    const size_t n = xs.size();
+    xs.resize(n + emitted);
+    const pbf_params p = toParams(config);
+    uint64_t nv = 0, n_out = 0;
+    const int rc = pbf_advance_scene_host(ctx, &p, &sc, reinterpret_cast<pbf_particle *>(xs.data()), n, xs.size(), &n_out, &nv);
+    if (rc != PBF_OK) {
+      xs.resize(n);  // the particles themselves are untouched on failure
+      raise("advance");
+    }
+    xs.resize(n_out);
     if (xs.empty()) {
-      std::cout << "Particles depleted" << std::endl;
+      std::cout << "Particles depleted" << std::endl;  // ompsph.hpp:122-126
       std::this_thread::sleep_for(std::chrono::milliseconds(5));
       return {};
     }
-    const pbf_params p = toParams(config);
-    uint64_t nv = 0;
-    if (pbf_advance_host(ctx, &p, reinterpret_cast<pbf_particle *>(xs.data()), xs.size(), &nv) != PBF_OK) raise("advance");
     sph::Result<T, N, V> r;
     if (nv) {
       r.mesh.vs.resize(nv); r.mesh.ns.resize(nv); r.mesh.cs.resize(nv);
       if (pbf_mesh_download(ctx, reinterpret_cast<float *>(r.mesh.vs.data()), reinterpret_cast<float *>(r.mesh.ns.data()),
                             reinterpret_cast<float *>(r.mesh.cs.data()), nv) != PBF_OK)
         raise("mesh download");
+    }
+    for (size_t i = 0; i < scene.queries.size(); ++i) {  // sph::QueryResult, sph.hpp:27-31
+      uint64_t count = 0;
+      pbf_query_result(ctx, uint32_t(i), nullptr, 0, &count);
+      std::vector<uint64_t> ids(count);
+      if (count && pbf_query_result(ctx, uint32_t(i), ids.data(), count, &count) != PBF_OK) raise("query");
+      r.queries.push_back({scene.queries[i].id, scene.queries[i].point, std::vector<T>(ids.begin(), ids.end())});
     }
     return r;
   }

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PBF_ABI_VERSION 1
+#define PBF_ABI_VERSION 2
 
 typedef enum pbf_status {
   PBF_OK = 0,
@@ -69,6 +69,37 @@ typedef struct pbf_params {
   int32_t surface_enabled; /* std::optional<McParams>::has_value() */
   pbf_mc_params surface;
 } pbf_params;
+
+/* sph::Scene — src/sph.hpp:56-80: the per-call scene dynamics of advance().  Positions are in the caller's
+ * (unscaled) units, like pbf_particle::position. */
+typedef struct pbf_well {   /* sph::Well   sph.hpp:56-60: radial force on particles closer than 75 units (ompsph.hpp:141-148) */
+  uint64_t tag;
+  float centre[3];
+  float force;
+} pbf_well;
+typedef struct pbf_source { /* sph::Source sph.hpp:62-67: emits a floor(sqrt(rate)) x ceil(sqrt(rate)) sheet per call (ompsph.hpp:93-104) */
+  uint64_t tag;             /* becomes the id of every emitted particle */
+  float centre[3];
+  float velocity[3];
+  float colour[4];
+  float rate;
+} pbf_source;
+typedef struct pbf_drain {  /* sph::Drain  sph.hpp:69-73: removes fluid closer than `width` to the centre (ompsph.hpp:106-118) */
+  uint64_t tag;
+  float centre[3];
+  float width, depth;       /* depth is unused by every reference backend */
+} pbf_drain;
+typedef struct pbf_query {  /* sph::Query  sph.hpp:22-25: ids of the fluid particles in the cell that holds `point` (ompsph.hpp:167-186) */
+  uint64_t id;
+  float point[3];
+} pbf_query;
+typedef struct pbf_scene {
+  const pbf_well *wells;     uint32_t n_wells;
+  const pbf_source *sources; uint32_t n_sources;
+  const pbf_drain *drains;   uint32_t n_drains;
+  const pbf_query *queries;  uint32_t n_queries;
+} pbf_scene;
+#define PBF_MAX_WELLS 16
 
 /* Grid derived once per step — ompsph.hpp:132-135 and sph.hpp:238-241. */
 typedef struct pbf_grid_info {
@@ -148,6 +179,15 @@ int pbf_set_stream(pbf_ctx *ctx, void *cuda_stream);
  * fetch the mesh with pbf_mesh_download.  n == 0 is PBF_OK and does nothing (ompsph.hpp:122-126). */
 int pbf_advance_host(pbf_ctx *ctx, const pbf_params *params, pbf_particle *xs, uint64_t n,
                      uint64_t *n_mesh_vertices);
+/* The same with a Scene (sph.hpp:75-80), i.e. the whole of advance(config, scene, xs): sources append particles
+ * (so xs needs `capacity` >= n + emitted), drains remove them, wells add their force to the prediction, queries are
+ * answered from the step's cell table.  *n_out = particles after the call.  scene == NULL is the empty scene.
+ * Returns PBF_ERR_CAPACITY (xs untouched) when the emitted particles do not fit. */
+int pbf_advance_scene_host(pbf_ctx *ctx, const pbf_params *params, const pbf_scene *scene, pbf_particle *xs,
+                           uint64_t n, uint64_t capacity, uint64_t *n_out, uint64_t *n_mesh_vertices);
+/* sph::QueryResult::neighbours (sph.hpp:27-31) of query `index` of the last step's scene, in Z-sorted order.
+ * *count receives the number of ids (also when ids == NULL or capacity is too small -> PBF_ERR_CAPACITY). */
+int pbf_query_result(pbf_ctx *ctx, uint32_t index, uint64_t *ids, uint64_t capacity, uint64_t *count);
 /* sph::ColouredMesh (sph.hpp:105-112): vs/ns = 3 floats per vertex, cs = 4 floats per vertex,
  * non-indexed, triangles ordered by marching-cube index.  Each pointer may be NULL to skip it. */
 int pbf_mesh_download(pbf_ctx *ctx, float *vs, float *ns, float *cs, uint64_t capacity_vertices);
@@ -155,6 +195,10 @@ int pbf_mesh_download(pbf_ctx *ctx, float *vs, float *ns, float *cs, uint64_t ca
 /* ---- resident path (no host round trip between steps) ------------------------------------------ */
 int pbf_upload(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n);
 int pbf_step(pbf_ctx *ctx, const pbf_params *params);          /* enqueue one step (asynchronous) */
+/* Scene of the following pbf_step calls (copied; NULL = empty).  Every step applies it the way every advance()
+ * call does: sources emit, drains remove (one host synchronisation per step while there are drains), wells pull,
+ * queries are answered (pbf_query_result after pbf_sync). */
+int pbf_set_scene(pbf_ctx *ctx, const pbf_scene *scene);
 int pbf_sync(pbf_ctx *ctx);
 int pbf_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_t *n_out);
 int pbf_particle_count(pbf_ctx *ctx, uint64_t *n_out);

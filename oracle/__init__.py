@@ -22,7 +22,7 @@ if str(HERE.parent) not in sys.path:
     sys.path.insert(0, str(HERE.parent))
 
 # the POD types of include/pbf_cuda.h have ONE Python definition, in the product's binding
-from pbf_sph_b200.capi import PARTICLE, GridInfo, McParams, Params  # noqa: E402,F401
+from pbf_sph_b200.capi import PARTICLE, GridInfo, McParams, Params, SceneStruct  # noqa: E402,F401
 
 GAUSS_SEIDEL = 1
 SKIP_DIFFUSE = 2
@@ -35,7 +35,8 @@ class OracleIO(C.Structure):
                 ("mc_field", C.c_void_p), ("mc_colour", C.c_void_p), ("mc_lattice_cap", C.c_uint64),
                 ("mesh_vs", C.c_void_p), ("mesh_ns", C.c_void_p), ("mesh_cs", C.c_void_p),
                 ("mesh_cap_vertices", C.c_uint64), ("forced_perm", C.c_void_p),
-                ("grid", GridInfo), ("n_vertices", C.c_uint64)]
+                ("grid", GridInfo), ("n_vertices", C.c_uint64),
+                ("scene", C.POINTER(SceneStruct)), ("query_first", C.c_void_p), ("query_count", C.c_void_p)]
 
 
 def build(verbose: bool = False) -> None:
@@ -58,6 +59,9 @@ def lib() -> C.CDLL:
                                          C.POINTER(OracleIO)]
         _lib.pbf_oracle_step.restype = C.c_int
         _lib.pbf_oracle_grid.argtypes = [C.c_float, C.POINTER(Params), C.POINTER(GridInfo)]
+        _lib.pbf_oracle_scene_edit.argtypes = [C.c_float, C.POINTER(Params), C.POINTER(SceneStruct), C.c_void_p,
+                                               C.c_uint64, C.c_uint64]
+        _lib.pbf_oracle_scene_edit.restype = C.c_int64
         _lib.pbf_oracle_morton_encode.argtypes = [C.c_uint32] * 3
         _lib.pbf_oracle_morton_encode.restype = C.c_uint32
     return _lib
@@ -69,8 +73,19 @@ def grid(h: float, params: Params) -> GridInfo:
     return g
 
 
+def scene_edit(h: float, params: Params, scene, xs: np.ndarray) -> np.ndarray:
+    """Sources then drains on the particle list (ompsph.hpp:91-120); returns the edited list."""
+    cap = len(xs) + scene.emitted()
+    buf = np.zeros(cap, PARTICLE)
+    buf[: len(xs)] = xs
+    n = lib().pbf_oracle_scene_edit(C.c_float(h), C.byref(params), C.byref(scene.struct), buf.ctypes.data, len(xs), cap)
+    if n < 0:
+        raise RuntimeError(f"pbf_oracle_scene_edit failed: {n}")
+    return buf[:n].copy()
+
+
 def step(h: float, params: Params, xs: np.ndarray, mode: int = 0, taps: bool = False, mesh: bool = True,
-         forced_perm: np.ndarray | None = None) -> dict:
+         forced_perm: np.ndarray | None = None, scene=None) -> dict:
     """One oracle step.  ``xs`` (PARTICLE array) is advanced IN PLACE into Z-sorted order.
 
     Returns a dict with the grid info and, when ``taps``, every intermediate the parity tests compare."""
@@ -108,6 +123,11 @@ def step(h: float, params: Params, xs: np.ndarray, mode: int = 0, taps: bool = F
             io.mesh_ns = buf("mesh_ns", (cap, 3), np.float32)
             io.mesh_cs = buf("mesh_cs", (cap, 4), np.float32)
             io.mesh_cap_vertices = cap
+    if scene is not None:  # wells act in the prediction, queries are answered from the cell table
+        io.scene = C.pointer(scene.struct)
+        if scene.queries:
+            io.query_first = buf("query_first", len(scene.queries), np.uint32)
+            io.query_count = buf("query_count", len(scene.queries), np.uint32)
     if forced_perm is not None:
         fp = np.ascontiguousarray(forced_perm, dtype=np.uint32)
         keep["_forced"] = fp
@@ -181,6 +201,31 @@ def ref_advance(h: float, params: Params, xs: np.ndarray, variant: str = "strict
         raise RuntimeError(f"pbf_ref_advance failed: {rc}")
     k = min(int(nv.value), mesh_cap)
     return {"n_vertices": int(nv.value), "mesh_vs": vs[:k], "mesh_ns": ns[:k], "mesh_cs": cs[:k]}
+
+
+def ref_advance_scene(h: float, params: Params, scene, xs: np.ndarray, variant: str = "strict", threads: int | None = None):
+    """advance(params, scene, xs) on the real reference; returns (particles after the call, [(query id, ids)])."""
+    L = ref_lib(variant)
+    if threads is not None:
+        L.pbf_ref_set_threads(threads)
+    cap = len(xs) + scene.emitted()
+    buf = np.zeros(cap, PARTICLE)
+    buf[: len(xs)] = xs
+    n_out = C.c_uint64(0)
+    q_ids = np.zeros(max(1, cap * max(1, len(scene.queries))), np.uint64)
+    q_counts = np.zeros(max(1, len(scene.queries)), np.uint64)
+    L.pbf_ref_advance_scene.argtypes = [C.c_float, C.POINTER(Params), C.POINTER(SceneStruct), C.c_void_p, C.c_uint64,
+                                        C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.c_void_p]
+    rc = L.pbf_ref_advance_scene(C.c_float(h), C.byref(params), C.byref(scene.struct), buf.ctypes.data, len(xs), cap,
+                                 C.byref(n_out), q_ids.ctypes.data, len(q_ids), q_counts.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"pbf_ref_advance_scene failed: {rc}")
+    res, w = [], 0
+    for i, q in enumerate(scene.queries):
+        c = int(q_counts[i])
+        res.append((q.id, q_ids[w:w + c].copy()))
+        w += c
+    return buf[: n_out.value].copy(), res
 
 
 def ref_scene_2cubes(count: int, solver_iter: int, scaling: float = 500.0, variant: str = "strict"):

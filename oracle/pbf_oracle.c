@@ -66,6 +66,11 @@ typedef struct pbf_oracle_io {
   /* results */
   pbf_grid_info grid;
   uint64_t n_vertices;
+  /* scene dynamics that act INSIDE the step: wells (ompsph.hpp:141-148) and queries (:167-186); NULL = empty scene.
+   * Sources and drains edit the particle list before the step: pbf_oracle_scene_edit. */
+  const pbf_scene *scene;
+  uint32_t *query_first; /* [scene->n_queries] first sorted index of the query's cell */
+  uint32_t *query_count; /* [scene->n_queries] particles in it (all Fluid: Obstacles are rejected) */
 } pbf_oracle_io;
 
 /* ---- curves.h:46-88 ------------------------------------------------------------------------------ */
@@ -185,15 +190,31 @@ int pbf_oracle_step(float h, const pbf_params *p, pbf_particle *xs, uint64_t n, 
   const uint64_t G = io->grid.grid_table_n;
   const uint32_t *ext = io->grid.extent;
 
-  /* ---- advect + key: ompsph.hpp:137-154 (no wells: drivers pass an empty Scene) ---- */
+  /* ---- advect + key: ompsph.hpp:137-154 ---- */
+  const uint32_t n_wells = io->scene ? io->scene->n_wells : 0u;
   float *vel_in = malloc(sizeof(float) * 3 * n), *pstar_in = malloc(sizeof(float) * 3 * n);
   uint64_t *composite = malloc(sizeof(uint64_t) * n);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)n; ++i) {
     const pbf_particle *q = &xs[i];
-    float key_arg[3];
+    float key_arg[3], combined[3];
+    for (int a = 0; a < 3; ++a) combined[a] = q->mass * p->constant_force[a];
+    for (uint32_t w = 0; w < n_wells; ++w) { /* ompsph.hpp:141-148 */
+      const pbf_well *well = &io->scene->wells[w];
+      const float dist = dist3(q->position, well->centre); /* glm::distance(p.position, well.centre) */
+      if (dist < 75.0f) {
+        float d[3];
+        for (int a = 0; a < 3; ++a) d[a] = well->centre[a] - q->position[a];
+        /* glm::normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x) */
+        const float inv = 1.0f / sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+        for (int a = 0; a < 3; ++a) {
+          const float fw = (((d[a] * inv) * well->force) * q->mass) / (dist * dist);
+          combined[a] += fmin_glm(fmax_glm(fw, -10.0f), 10.0f); /* glm::clamp = min(max(x, lo), hi) */
+        }
+      }
+    }
     for (int a = 0; a < 3; ++a) {
-      const float force = q->mass * p->constant_force[a];
+      const float force = combined[a];
       const float v = force * dt + q->velocity[a];
       const float ps = (v * dt) + (q->position[a] / scale);
       vel_in[3 * i + a] = v;
@@ -253,6 +274,21 @@ int pbf_oracle_step(float h, const pbf_params *p, pbf_particle *xs, uint64_t n, 
     if (io->cell_table_cap < G) return PBF_ERR_CAPACITY;
     memcpy(io->cell_table, table, sizeof(uint32_t) * G);
   }
+
+  /* ---- queries: ompsph.hpp:167-186 (one cell per query; the neighbours are the ids of that sorted range) ---- */
+  if (io->scene && io->scene->n_queries && io->query_first && io->query_count)
+    for (uint32_t qi = 0; qi < io->scene->n_queries; ++qi) {
+      const pbf_query *qq = &io->scene->queries[qi];
+      float r[3];
+      for (int a = 0; a < 3; ++a) r[a] = (qq->point[a] / scale) - minE[a];
+      const uint64_t z = key_at(r[0], r[1], r[2], h);
+      io->query_first[qi] = 0;
+      io->query_count[qi] = 0;
+      if (z < G && z + 1 < G) {
+        io->query_first[qi] = table[z];
+        io->query_count[qi] = table[z + 1] - table[z];
+      }
+    }
 
   /* ---- tap: candidate / in-radius counts on the predicted positions (what the first lambda pass sees) ---- */
   if (io->cand_count || io->nbr_count) {
@@ -518,6 +554,45 @@ int pbf_oracle_step(float h, const pbf_params *p, pbf_particle *xs, uint64_t n, 
 }
 
 /* Solver constants as the oracle forms them (so tests can compare the host side of the product bit for bit). */
+/* Sources then drains on the caller's particle list — ompsph.hpp:91-120.  Returns the new count, or a negative
+ * pbf_status when the emitted particles do not fit `cap`. */
+int64_t pbf_oracle_scene_edit(float h, const pbf_params *p, const pbf_scene *scene, pbf_particle *xs, uint64_t n,
+                              uint64_t cap) {
+  if (!scene) return (int64_t)n;
+  const float spacing = (h * p->scale / 2);
+  for (uint32_t si = 0; si < scene->n_sources; ++si) {
+    const pbf_source *src = &scene->sources[si];
+    const float size = sqrtf(src->rate);
+    const uint64_t width = (uint64_t)floorf(size), depth = (uint64_t)ceilf(size);
+    /* offset = centre - (V3(width, 0, depth) * 0.5 * spacing) */
+    const float off[3] = {src->centre[0] - (((float)width * 0.5f) * spacing), src->centre[1] - ((0.0f * 0.5f) * spacing),
+                          src->centre[2] - (((float)depth * 0.5f) * spacing)};
+    for (uint64_t x = 0; x < width; ++x)
+      for (uint64_t z = 0; z < depth; ++z) {
+        if (n >= cap) return PBF_ERR_CAPACITY;
+        pbf_particle *q = &xs[n++];
+        memset(q, 0, sizeof(*q));
+        q->id = src->tag;
+        q->type = PBF_TYPE_FLUID;
+        q->mass = 1.0f;
+        q->position[0] = off[0] + ((float)x * spacing);
+        q->position[1] = off[1] + (0.0f * spacing);
+        q->position[2] = off[2] + ((float)z * spacing);
+        for (int a = 0; a < 3; ++a) q->velocity[a] = src->velocity[a];
+        for (int a = 0; a < 4; ++a) q->colour[a] = src->colour[a];
+      }
+  }
+  uint64_t kept = 0;
+  for (uint64_t i = 0; i < n; ++i) { /* std::remove_if keeps the survivors' order */
+    int drained = 0;
+    if (xs[i].type != PBF_TYPE_OBSTACLE)
+      for (uint32_t di = 0; di < scene->n_drains && !drained; ++di)
+        if (dist3(scene->drains[di].centre, xs[i].position) < scene->drains[di].width) drained = 1;
+    if (!drained) xs[kept++] = xs[i];
+  }
+  return (int64_t)kept;
+}
+
 void pbf_oracle_constants(float h, float out[3]) {
   out[0] = poly6_factor(h);
   out[1] = spiky_factor(h);

@@ -133,6 +133,73 @@ int pbf_ref_advance(float h, const pbf_params *p, pbf_particle *xs, uint64_t n, 
   return rc;
 }
 
+// The same with a Scene (sph.hpp:75-80): xs has room for `cap` particles, *n_out = particles after the call; the
+// query results (ids) are written back to back into q_ids (cap q_ids_cap), q_counts[i] = ids of query i.
+int pbf_ref_advance_scene(float h, const pbf_params *p, const pbf_scene *sc, pbf_particle *xs, uint64_t n, uint64_t cap,
+                          uint64_t *n_out, uint64_t *q_ids, uint64_t q_ids_cap, uint64_t *q_counts) {
+  std::vector<Particle> ps;
+  ps.reserve(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    const pbf_particle &q = xs[i];
+    ps.emplace_back(size_t(q.id), static_cast<sph::Type>(q.type), q.mass,
+                    V<4, float>(q.colour[0], q.colour[1], q.colour[2], q.colour[3]),
+                    V<3, float>(q.position[0], q.position[1], q.position[2]),
+                    V<3, float>(q.velocity[0], q.velocity[1], q.velocity[2]));
+  }
+  sph::Scene<size_t, float, V> scene{};
+  if (sc) {
+    for (uint32_t i = 0; i < sc->n_wells; ++i)
+      scene.wells.push_back({size_t(sc->wells[i].tag),
+                             V<3, float>(sc->wells[i].centre[0], sc->wells[i].centre[1], sc->wells[i].centre[2]),
+                             sc->wells[i].force});
+    for (uint32_t i = 0; i < sc->n_sources; ++i) {
+      const pbf_source &s = sc->sources[i];
+      scene.sources.push_back({size_t(s.tag), V<3, float>(s.centre[0], s.centre[1], s.centre[2]),
+                               V<3, float>(s.velocity[0], s.velocity[1], s.velocity[2]),
+                               V<4, float>(s.colour[0], s.colour[1], s.colour[2], s.colour[3]), s.rate});
+    }
+    for (uint32_t i = 0; i < sc->n_drains; ++i)
+      scene.drains.push_back({size_t(sc->drains[i].tag),
+                              V<3, float>(sc->drains[i].centre[0], sc->drains[i].centre[1], sc->drains[i].centre[2]),
+                              sc->drains[i].width, sc->drains[i].depth});
+    for (uint32_t i = 0; i < sc->n_queries; ++i)
+      scene.queries.push_back({size_t(sc->queries[i].id),
+                               V<3, float>(sc->queries[i].point[0], sc->queries[i].point[1], sc->queries[i].point[2])});
+  }
+  std::ostringstream sink;
+  std::streambuf *old = std::cout.rdbuf(sink.rdbuf());
+  int rc = 0;
+  try {
+    sph::omp_impl::Solver<size_t, float> solver(h);
+    auto result = solver.advance(to_ref(*p), scene, ps);
+    std::cout.rdbuf(old);
+    if (n_out) *n_out = ps.size();
+    if (ps.size() > cap) return -5;
+    for (uint64_t i = 0; i < ps.size(); ++i) {
+      pbf_particle &q = xs[i];
+      std::memset(&q, 0, sizeof(q));
+      q.id = ps[i].id;
+      q.type = uint8_t(ps[i].type);
+      q.mass = ps[i].mass;
+      q.position[0] = ps[i].position.x; q.position[1] = ps[i].position.y; q.position[2] = ps[i].position.z;
+      q.velocity[0] = ps[i].velocity.x; q.velocity[1] = ps[i].velocity.y; q.velocity[2] = ps[i].velocity.z;
+      q.colour[0] = ps[i].colour.x; q.colour[1] = ps[i].colour.y; q.colour[2] = ps[i].colour.z; q.colour[3] = ps[i].colour.w;
+    }
+    uint64_t w = 0;
+    for (size_t i = 0; i < result.queries.size(); ++i) {
+      if (q_counts) q_counts[i] = result.queries[i].neighbours.size();
+      for (size_t id : result.queries[i].neighbours) {
+        if (q_ids && w < q_ids_cap) q_ids[w] = id;
+        ++w;
+      }
+    }
+  } catch (...) {
+    std::cout.rdbuf(old);
+    rc = -2;
+  }
+  return rc;
+}
+
 // The reference's scene factory (sph.hpp:160-186) + wall motion (sph.hpp:147-158), for fixture generation.
 uint64_t pbf_ref_scene_2cubes(uint64_t count, uint64_t solver_iter, float scaling, pbf_params *out_p,
                               pbf_particle *xs, uint64_t cap) {

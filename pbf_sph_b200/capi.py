@@ -68,10 +68,60 @@ class DistStats(C.Structure):
                 ("key_hi", C.c_uint32), ("ghost_ring1", C.c_uint32), ("boundary", C.c_uint32)]
 
 
+class Well(C.Structure):  # sph::Well — sph.hpp:56-60
+    _fields_ = [("tag", C.c_uint64), ("centre", C.c_float * 3), ("force", C.c_float)]
+
+
+class Source(C.Structure):  # sph::Source — sph.hpp:62-67
+    _fields_ = [("tag", C.c_uint64), ("centre", C.c_float * 3), ("velocity", C.c_float * 3), ("colour", C.c_float * 4),
+                ("rate", C.c_float)]
+
+
+class Drain(C.Structure):  # sph::Drain — sph.hpp:69-73
+    _fields_ = [("tag", C.c_uint64), ("centre", C.c_float * 3), ("width", C.c_float), ("depth", C.c_float)]
+
+
+class Query(C.Structure):  # sph::Query — sph.hpp:22-25
+    _fields_ = [("id", C.c_uint64), ("point", C.c_float * 3)]
+
+
+class SceneStruct(C.Structure):  # pbf_scene
+    _fields_ = [("wells", C.POINTER(Well)), ("n_wells", C.c_uint32), ("sources", C.POINTER(Source)),
+                ("n_sources", C.c_uint32), ("drains", C.POINTER(Drain)), ("n_drains", C.c_uint32),
+                ("queries", C.POINTER(Query)), ("n_queries", C.c_uint32)]
+
+
+class Scene:
+    """sph::Scene — sph.hpp:75-80: python lists in, one pbf_scene (with the arrays kept alive) out."""
+
+    def __init__(self, wells=(), sources=(), drains=(), queries=()):
+        self.wells = [Well(t, (C.c_float * 3)(*c), f) for t, c, f in wells]
+        self.sources = [Source(t, (C.c_float * 3)(*c), (C.c_float * 3)(*v), (C.c_float * 4)(*col), r)
+                        for t, c, v, col, r in sources]
+        self.drains = [Drain(t, (C.c_float * 3)(*c), w, d) for t, c, w, d in drains]
+        self.queries = [Query(i, (C.c_float * 3)(*pt)) for i, pt in queries]
+        self._arrays = ((Well * len(self.wells))(*self.wells), (Source * len(self.sources))(*self.sources),
+                        (Drain * len(self.drains))(*self.drains), (Query * len(self.queries))(*self.queries))
+        a = self._arrays
+        self.struct = SceneStruct(C.cast(a[0], C.POINTER(Well)), len(self.wells), C.cast(a[1], C.POINTER(Source)),
+                                  len(self.sources), C.cast(a[2], C.POINTER(Drain)), len(self.drains),
+                                  C.cast(a[3], C.POINTER(Query)), len(self.queries))
+
+    def emitted(self) -> int:
+        """Particles the sources emit per call: floor(sqrt(rate)) * ceil(sqrt(rate)) each (ompsph.hpp:93-104)."""
+        import math
+        total = 0
+        for s in self.sources:
+            side = float(np.sqrt(np.float32(s.rate)))
+            total += int(math.floor(side)) * int(math.ceil(side))
+        return total
+
+
 # every symbol include/pbf_cuda.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = [
     "pbf_create", "pbf_destroy", "pbf_last_error", "pbf_abi_version", "pbf_set_flags", "pbf_set_stream",
-    "pbf_advance_host", "pbf_mesh_download", "pbf_upload", "pbf_step", "pbf_sync", "pbf_download",
+    "pbf_advance_host", "pbf_advance_scene_host", "pbf_query_result", "pbf_set_scene", "pbf_mesh_download", "pbf_upload",
+    "pbf_step", "pbf_sync", "pbf_download",
     "pbf_particle_count", "pbf_device_state", "pbf_grid", "pbf_debug_read", "pbf_profile_reset", "pbf_profile_read",
     "pbf_launch_count", "pbf_dist_unique_id", "pbf_dist_init", "pbf_dist_init_local", "pbf_dist_upload",
     "pbf_dist_step", "pbf_dist_download", "pbf_dist_set_replan", "pbf_dist_stats_read", "pbf_host_alloc", "pbf_host_free", "pbf_host_grid",
@@ -107,6 +157,9 @@ def lib() -> C.CDLL:
         "pbf_set_flags": ([vp, u32], i32),
         "pbf_set_stream": ([vp, vp], i32),
         "pbf_advance_host": ([vp, P(Params), vp, u64, P(u64)], i32),
+        "pbf_advance_scene_host": ([vp, P(Params), P(SceneStruct), vp, u64, u64, P(u64), P(u64)], i32),
+        "pbf_query_result": ([vp, u32, vp, u64, P(u64)], i32),
+        "pbf_set_scene": ([vp, P(SceneStruct)], i32),
         "pbf_mesh_download": ([vp, vp, vp, vp, u64], i32),
         "pbf_upload": ([vp, vp, u64], i32),
         "pbf_step": ([vp, P(Params)], i32),

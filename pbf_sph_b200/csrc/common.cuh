@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "pbf_cuda.h"
 
@@ -63,6 +64,9 @@ struct StepConst {
   float sp_rho;             // SP * RHO_RECIP
   float p6_over_dq;         // P6 / P6dq
   float inv_rho;            // 1 / RHO
+  // scene wells (ompsph.hpp:141-148): centre.xyz | force, device array
+  uint32_t n_wells;
+  const float4 *wells;
 };
 
 struct McConst {
@@ -94,9 +98,28 @@ __device__ __forceinline__ void predict(const StepConst &c, const float4 pos_mas
   const float p[3] = {pos_mass.x, pos_mass.y, pos_mass.z};
   const float v[3] = {vel.x, vel.y, vel.z};
   uint32_t cc[3];
+  float force[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) force[a] = fmul(pos_mass.w, c.force[a]);
+  // wells — ompsph.hpp:141-148: within 75 units, force += clamp((normalize(centre - pos) * well.force * mass) / dist^2,
+  // -10, 10); glm::distance/normalize/clamp as in glm 0.9.9.8 (dot = (x*x + y*y) + z*z, inversesqrt = 1 / sqrt)
+  for (uint32_t w = 0; w < c.n_wells; ++w) {
+    const float4 well = __ldg(c.wells + w);
+    const float d[3] = {fsub(well.x, p[0]), fsub(well.y, p[1]), fsub(well.z, p[2])};
+    const float dot = fadd(fadd(fmul(d[0], d[0]), fmul(d[1], d[1])), fmul(d[2], d[2]));
+    const float dist = fsqrt(dot);
+    if (dist < 75.0f) {
+      const float inv = fdiv(1.0f, fsqrt(dot)), dd = fmul(dist, dist);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float fw = fdiv(fmul(fmul(fmul(d[a], inv), well.w), pos_mass.w), dd);
+        force[a] = fadd(force[a], glm_min(glm_max(fw, -10.0f), 10.0f));
+      }
+    }
+  }
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const float f = fmul(pos_mass.w, c.force[a]);
+    const float f = force[a];
     v_out[a] = fadd(fmul(f, c.dt), v[a]);
     ps_out[a] = fadd(fmul(v_out[a], c.dt), fdiv(p[a], c.scale));
     cc[a] = cell_coord(fdiv(fsub(ps_out[a], c.min_extent[a]), c.h));
@@ -135,6 +158,20 @@ template <typename T> struct DevBuf {
 };
 
 }  // namespace pbf
+
+// ---- scene dynamics of advance() (scene.cu) -------------------------------------------------------------------
+struct pbf_scene_state {
+  std::vector<pbf_well> wells;
+  std::vector<pbf_source> sources;
+  std::vector<pbf_drain> drains;
+  std::vector<pbf_query> queries;
+  pbf::DevBuf<float4> d_wells, d_drains, d_queries;  // centre.xyz | force / width / 0
+  pbf::DevBuf<uint2> d_ranges;                       // per query: first particle, count (Z-sorted order)
+  uint2 *h_ranges = nullptr;                         // pinned mirror, valid after a stream sync
+  size_t h_ranges_cap = 0;
+  uint32_t answered = 0;                             // queries answered by the last step
+  bool empty() const { return wells.empty() && sources.empty() && drains.empty() && queries.empty(); }
+};
 
 // ---- the context -----------------------------------------------------------------------------------
 struct pbf_ctx {
@@ -190,6 +227,8 @@ struct pbf_ctx {
   // 0: thread-per-particle search walking the cell table (neighbour_list.cu, the production form);
   // 1: warp-per-cell search over the per-step plan (cell_search.cu, PBF_SEARCH=cells).  Both write the same lists.
   int search_mode = 0;
+
+  pbf_scene_state scene;
 
   pbf_grid_info grid{};
   pbf::StepConst sc{};
@@ -291,6 +330,12 @@ int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t
 int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col);
 
 void dist_release(pbf_ctx *ctx);  // dist.cu
+// scene dynamics (scene.cu)
+int scene_set(pbf_ctx *ctx, const pbf_scene *scene);
+int scene_edit_particles(pbf_ctx *ctx, const pbf_params &p);  // sources, then drains, on the resident particles
+int scene_answer_queries(pbf_ctx *ctx);                       // after the cell table of a step
+void scene_emit(float h, float scale, const std::vector<pbf_source> &sources, std::vector<pbf_particle> &out);
+void scene_release(pbf_ctx *ctx);
 
 inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 

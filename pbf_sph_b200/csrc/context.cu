@@ -12,6 +12,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace pbf {
@@ -151,14 +153,21 @@ static int validate(pbf_ctx *ctx, const pbf_params *p) {
 }
 
 static int step_device(pbf_ctx *ctx, const pbf_params &p) {
+  if (!ctx->scene.empty()) {
+    PBF_TRY(validate(ctx, &p));
+    PBF_TRY(scene_edit_particles(ctx, p));  // sources, then drains (ompsph.hpp:91-120)
+  }
+  ctx->scene.answered = 0;
   const uint64_t n64 = ctx->n;
-  if (n64 == 0) return PBF_OK;
+  if (n64 == 0) return PBF_OK;  // "Particles depleted" (ompsph.hpp:122-126)
   if (n64 >= 0xFFFFFFF0ull) return fail(ctx, PBF_ERR_INVALID, "n", "more than 2^32 particles on one device");
   const uint32_t n = (uint32_t)n64;
   PBF_TRY(validate(ctx, &p));
   host_grid(ctx->h, p, ctx->grid);
   ctx->grid.n_particles = n;
   host_step_const(ctx->h, p, ctx->grid, n, ctx->sc);
+  ctx->sc.n_wells = (uint32_t)ctx->scene.wells.size();
+  ctx->sc.wells = ctx->scene.d_wells.p;
   const int o = ctx->cur ^ 1, oc = ctx->cur_col ^ 1;
   PBF_CUDA(ctx, ctx->pos[o].reserve(n));
   PBF_CUDA(ctx, ctx->vel[o].reserve(n));
@@ -178,6 +187,7 @@ static int step_device(pbf_ctx *ctx, const pbf_params &p) {
   ctx->cur = o;
   ctx->cur_col = oc;
   PBF_TRY(launch_cell_table(ctx, ctx->keys_sorted, ctx->table.p));
+  PBF_TRY(scene_answer_queries(ctx));  // ompsph.hpp:167-186
   const bool tiled = !(ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS);
   if (ctx->flags & PBF_FLAG_DEBUG_COUNTS) {
     PBF_CUDA(ctx, ctx->cand_count.reserve(n));
@@ -301,6 +311,7 @@ void pbf_destroy(pbf_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   dist_release(ctx);
+  scene_release(ctx);
   for (int i = 0; i < 2; ++i) {
     ctx->pos[i].release(); ctx->vel[i].release(); ctx->col[i].release(); ctx->ids[i].release(); ctx->pstar[i].release();
   }
@@ -346,24 +357,60 @@ int pbf_set_stream(pbf_ctx *ctx, void *cuda_stream) {
   return PBF_OK;
 }
 
-int pbf_advance_host(pbf_ctx *ctx, const pbf_params *params, pbf_particle *xs, uint64_t n, uint64_t *n_mesh_vertices) {
+int pbf_advance_scene_host(pbf_ctx *ctx, const pbf_params *params, const pbf_scene *scene, pbf_particle *xs, uint64_t n,
+                           uint64_t capacity, uint64_t *n_out, uint64_t *n_mesh_vertices) {
   PBF_ENTER(ctx);
   if (n_mesh_vertices) *n_mesh_vertices = 0;
+  if (n_out) *n_out = n;
   if (ctx->dist) return fail(ctx, PBF_ERR_STATE, "pbf_advance_host", "this context is a slab rank: use pbf_dist_step");
-  if (n == 0) { ctx->n = 0; return PBF_OK; }  // ompsph.hpp:122-126: nothing to do
-  if (!xs) return fail(ctx, PBF_ERR_INVALID, "xs", "NULL");
+  if (!ctx->scene.empty() || scene) PBF_TRY(scene_set(ctx, scene));
+  if (n && !xs) return fail(ctx, PBF_ERR_INVALID, "xs", "NULL");
   PBF_TRY(validate(ctx, params));
+  if (!ctx->scene.sources.empty()) {  // the emitted particles must fit the caller's array
+    std::vector<pbf_particle> fresh;
+    scene_emit(ctx->h, params->scale, ctx->scene.sources, fresh);
+    if (n + fresh.size() > capacity) return fail(ctx, PBF_ERR_CAPACITY, "xs", "capacity too small for the particles the sources emit");
+    if (!xs && !fresh.empty()) return fail(ctx, PBF_ERR_INVALID, "xs", "NULL");
+  }
   PBF_TRY(upload_device(ctx, xs, n));
   PBF_TRY(step_device(ctx, *params));
   // the type check result is known only now; the particle array is left untouched on failure
   PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (*ctx->flag_host) {
+  if (n && *ctx->flag_host) {
     ctx->n = 0; ctx->have_state = false;
     return fail(ctx, PBF_ERR_INVALID, "xs", "Obstacle particles are not supported (the reference OMP backend drops them)");
   }
-  PBF_TRY(download_device(ctx, xs, n));
+  if (n_out) *n_out = ctx->n;
+  if (ctx->n == 0) return PBF_OK;  // ompsph.hpp:122-126: nothing to do / particles depleted
+  PBF_TRY(download_device(ctx, xs, ctx->n));
   PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (n_mesh_vertices) *n_mesh_vertices = ctx->n_triangles * 3;
+  return PBF_OK;
+}
+
+int pbf_advance_host(pbf_ctx *ctx, const pbf_params *params, pbf_particle *xs, uint64_t n, uint64_t *n_mesh_vertices) {
+  return pbf_advance_scene_host(ctx, params, nullptr, xs, n, n, nullptr, n_mesh_vertices);
+}
+
+int pbf_set_scene(pbf_ctx *ctx, const pbf_scene *scene) {
+  PBF_ENTER(ctx);
+  if (ctx->dist && scene && (scene->n_wells || scene->n_sources || scene->n_drains || scene->n_queries))
+    return fail(ctx, PBF_ERR_STATE, "pbf_set_scene", "scene dynamics are not available on the slab path");
+  return scene_set(ctx, scene);
+}
+
+int pbf_query_result(pbf_ctx *ctx, uint32_t index, uint64_t *ids, uint64_t capacity, uint64_t *count) {
+  PBF_ENTER(ctx);
+  if (count) *count = 0;
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (index >= ctx->scene.answered) return fail(ctx, PBF_ERR_INVALID, "index", "no such query in the last step");
+  const uint2 r = ctx->scene.h_ranges[index];
+  if (count) *count = r.y;
+  if (r.y == 0) return PBF_OK;
+  if (!ids || capacity < r.y) return fail(ctx, PBF_ERR_CAPACITY, "pbf_query_result", "ids too small");
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "id width");
+  PBF_CUDA(ctx, cudaMemcpyAsync(ids, ctx->ids[ctx->cur].p + r.x, (size_t)r.y * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PBF_OK;
 }
 

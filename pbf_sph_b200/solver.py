@@ -15,10 +15,11 @@ from .capi import PARTICLE, GridInfo, Params, Profile, check, lib
 
 
 @dataclass
-class Result:  # sph::Result — sph.hpp:114-117 (queries are out of scope: drivers pass an empty Scene)
+class Result:  # sph::Result — sph.hpp:114-117
     vs: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
     ns: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
     cs: np.ndarray = field(default_factory=lambda: np.zeros((0, 4), np.float32))
+    queries: list = field(default_factory=list)  # [(query id, ids of the fluid particles in its cell)] — sph.hpp:27-31
 
 
 class Solver:
@@ -58,6 +59,35 @@ class Solver:
         nv = C.c_uint64(0)
         self._ck(self._L.pbf_advance_host(self._ctx, C.byref(params), xs.ctypes.data, len(xs), C.byref(nv)))
         return self.mesh() if (mesh and nv.value) else Result()
+
+    def advance_scene(self, params: Params, scene, xs: np.ndarray, mesh: bool = True):
+        """advance(config, scene, xs) with a non-empty sph::Scene (capi.Scene): returns (xs after the call — sources
+        may have appended, drains removed —, Result with the query answers)."""
+        assert xs.dtype == PARTICLE and xs.flags.c_contiguous
+        cap = len(xs) + scene.emitted()
+        buf = np.zeros(cap, PARTICLE)
+        buf[: len(xs)] = xs
+        nv, n_out = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self._L.pbf_advance_scene_host(self._ctx, C.byref(params), C.byref(scene.struct), buf.ctypes.data, len(xs),
+                                                cap, C.byref(n_out), C.byref(nv)))
+        res = self.mesh() if (mesh and nv.value) else Result()
+        res.queries = self.query_results(scene) if n_out.value else [(q.id, np.zeros(0, np.uint64)) for q in scene.queries]
+        return buf[: n_out.value], res
+
+    def set_scene(self, scene) -> None:
+        """Scene of the following step() calls on the resident path (None = empty)."""
+        self._ck(self._L.pbf_set_scene(self._ctx, C.byref(scene.struct) if scene is not None else None))
+
+    def query_results(self, scene) -> list:
+        out = []
+        for i, q in enumerate(scene.queries):
+            cnt = C.c_uint64(0)
+            self._L.pbf_query_result(self._ctx, i, None, 0, C.byref(cnt))  # count only (CAPACITY status when > 0)
+            ids = np.zeros(cnt.value, np.uint64)
+            if cnt.value:
+                self._ck(self._L.pbf_query_result(self._ctx, i, ids.ctypes.data, cnt.value, C.byref(cnt)))
+            out.append((q.id, ids))
+        return out
 
     def advance_ptr(self, params: Params, ptr: int, n: int) -> int:
         """advance() on a raw host pointer (e.g. pinned memory); returns the mesh vertex count."""

@@ -36,7 +36,7 @@ using Result = sph::Result<size_t, float, pbf::vec>;
 struct Options {
   std::string impl = "cuda", output = "./out_{impl}_{type}_{iter}", scene = "2cubes", device = "0";
   size_t iterations = 200, warmup = 200, particles = 20000, solverIter = 6;
-  bool list = false, verbose = false, fp64 = false, surface = true, resident = false, help = false;
+  bool list = false, verbose = false, fp64 = false, surface = true, resident = false, fountain = false, help = false;
 };
 
 static void usage() {
@@ -53,6 +53,8 @@ static void usage() {
                "                              {iter}, {impl}, {type}. Default: ./out_{impl}_{type}_{iter}\n"
                "      --scene=[2cubes|dam]    Stock two-cube scene with the moving wall, or a dam-break block\n"
                "      --particles=[N]         Particle budget of the scene. Default: 20000\n"
+               "      --fountain              Pass a non-empty sph::Scene to every advance(): a well, a source, a drain and\n"
+               "                              two queries (the scene of tests/helpers.py demo_scene)\n"
                "      --solver-iters=[I]      Solver iterations per step. Default: 6\n"
                "      --surface=[on|off]      Marching-cubes surface extraction each frame. Default: on\n"
                "      --resident              Keep particles on the device between frames\n";
@@ -82,6 +84,7 @@ static Options parse(int argc, char **argv) {
     else if (a == "-v" || a == "--verbose") o.verbose = true;
     else if (a == "--fp64") o.fp64 = true;
     else if (a == "--resident") o.resident = true;
+    else if (a == "--fountain") o.fountain = true;
     else if (take(argc, argv, i, "i", "impl", v)) o.impl = v;
     else if (take(argc, argv, i, "d", "devices", v)) o.device = v;
     else if (take(argc, argv, i, "n", "iter", v)) o.iterations = std::stoull(v);
@@ -159,10 +162,20 @@ int main(int argc, char *argv[]) {
                              << " surface=" << (o.surface ? "on" : "off") << " resident=" << o.resident << std::endl;
     std::cout << "Using " << output << " for output" << std::endl;
     Result result;
+    sph::Scene<size_t, float, pbf::vec> scene{};  // both reference drivers pass an empty Scene (benchmark.cpp:33,47)
+    if (o.fountain) {
+      using V3 = pbf::vec<3, float>;
+      scene.wells.push_back({7, V3(300, 200, 300), 5000.0f});
+      scene.sources.push_back({99, V3(500, 100, 500), V3(0, 1, 0), pbf::vec<4, float>(1, 0, 0, 1), 20.0f});
+      scene.drains.push_back({1, V3(120, 20, 120), 40.0f, 1.0f});
+      scene.queries.push_back({11, V3(150, 60, 150)});
+      scene.queries.push_back({12, V3(900, 900, 900)});
+      if (o.resident) throw std::runtime_error("--fountain goes through advance(config, scene, xs): not with --resident");
+    }
     auto frameParams = [&](size_t frame) { return moving ? sph::applyMotionSinXCosZ(param, frame) : param; };
     auto advance = [&](size_t frame, const char *what) {
       try {
-        if (!o.resident) { result = solver.advance(frameParams(frame), {}, particles); return; }
+        if (!o.resident) { result = solver.advance(frameParams(frame), scene, particles); return; }
         const pbf_params p = decltype(solver)::toParams(frameParams(frame));
         if (pbf_step(solver.handle(), &p) != PBF_OK || pbf_sync(solver.handle()) != PBF_OK)
           throw std::runtime_error(pbf_last_error(solver.handle()));
@@ -209,6 +222,7 @@ int main(int argc, char *argv[]) {
               << "Frame-time stdDev     : " << std::sqrt(var / frames) << " ms\n"
               << "Final Vertex count   : " << result.mesh.vs.size() << "\n"
               << "Final Particle count : " << particles.size() << " \n"
+              << "Query answers        :" << [&] { std::string q; for (const auto &a : result.queries) q += " " + std::to_string(a.id) + ":" + std::to_string(a.neighbours.size()); return q.empty() ? std::string(" none") : q; }() << "\n"
               << "Particle-iterations/s: " << double(particles.size()) * double(o.solverIter) * double(o.iterations) / seconds << "\n"
               << std::endl;
     save(result, particles, output);

@@ -19,7 +19,7 @@ def test_every_declared_symbol_is_exported():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
-    assert L.pbf_abi_version() == 1
+    assert L.pbf_abi_version() == 2
 
 
 def test_struct_layouts():

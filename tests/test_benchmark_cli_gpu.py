@@ -52,3 +52,25 @@ def test_benchmark_flags(gpu, tmp_path):
     assert "CUDA device 0" in run("-l").stdout
     out = run("--scene=dam", "--particles=27000", "--solver-iters=4", "--surface=off", "--resident", "-n3", "-w2", "-o", "")
     assert out.returncode == 0 and "Final Particle count : 27000" in out.stdout and "Final Vertex count   : 0" in out.stdout
+
+
+def test_benchmark_with_a_scene_matches_python_mirror(gpu, tmp_path):
+    """--fountain: a non-empty sph::Scene through sph::cuda_impl::Solver::advance (sources resize the caller's vector,
+    drains shrink it, Result::queries is filled) — same frames through the Python mirror give the same particles."""
+    from helpers import demo_scene
+    out = run("--fountain", "--particles=2000", "--solver-iters=3", "--surface=off", "-n", "4", "-w", "2", "-o",
+              str(tmp_path / "f_{iter}"))
+    assert out.returncode == 0, out.stdout + out.stderr
+    sc = demo_scene()
+    p, xs = scenes.two_cubes(2000, 3)
+    with Solver(scenes.H, 0) as s:
+        for f in list(range(2)) + list(range(4)):
+            xs, res = s.advance_scene(scenes.apply_motion(p, f), sc, xs)
+    assert f"Final Particle count : {len(xs)} " in out.stdout, out.stdout
+    want = " ".join(f"{qid}:{len(ids)}" for qid, ids in res.queries)
+    assert f"Query answers        : {want}" in out.stdout, out.stdout
+    raw = (tmp_path / "f_4" / "cloud.ply").read_bytes()
+    body = raw[raw.index(b"end_header\n") + len(b"end_header\n"):]
+    rec = np.frombuffer(body, dtype=np.dtype([("xyz", "<f4", 3), ("rgba", "<f4", 4), ("id", "<u4")]))
+    assert np.array_equal(rec["id"], xs["id"].astype(np.uint32)) and np.array_equal(rec["xyz"], xs["position"])
+    assert run("--fountain", "--resident", "-n1", "-w0", "-o", "").returncode != 0

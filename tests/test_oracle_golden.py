@@ -44,6 +44,24 @@ def test_small_scene_matches_unmodified_reference(oracle_mod, frame):
         assert close_or_equal(out[f"mesh_{k}"], g[f"f{frame}_{k}"], 1e-3), k
 
 
+@pytest.mark.parametrize("call", [0, 5])
+def test_scene_dynamics_match_reference_golden(oracle_mod, call):
+    """advance() with a well, a source, a drain and two queries: particle list (count, order, ids) and query answers
+    exactly as the real reference produced them; floats to the libm tolerance above."""
+    from helpers import demo_scene
+    g = np.load(GOLD / "scene_2cubes.npz")
+    p = params_from(g["params"], oracle_mod)
+    sc = demo_scene()
+    xs = oracle_mod.scene_edit(H, p, sc, g[f"c{call}_in"].copy())
+    t = oracle_mod.step(H, p, xs, mode=oracle_mod.GAUSS_SEIDEL, taps=True, scene=sc)
+    want = g[f"c{call}_out"]
+    assert len(xs) == len(want) and np.array_equal(xs["id"], want["id"])
+    for f in ("position", "velocity", "colour"):
+        assert close_or_equal(xs[f], want[f], 1e-3), f
+    for q, first, cnt in zip(sc.queries, t["query_first"], t["query_count"]):
+        assert np.array_equal(xs["id"][first:first + cnt], g[f"c{call}_q{q.id}"]), q.id
+
+
 def test_small_scene_bit_exact_on_generating_cpu(oracle_mod):
     """Strict form of the above; only asserted when the float results agree exactly on this CPU's libm."""
     g = np.load(GOLD / "small_2cubes.npz")

@@ -30,6 +30,27 @@ def test_gauss_seidel_mode_equals_reference_with_stable_sort(oracle_mod):
             assert np.array_equal(r[k], o[k], equal_nan=True), k
 
 
+def test_scene_dynamics_equal_reference(oracle_mod):
+    """Wells, sources, drains and queries (sph.hpp:56-80, ompsph.hpp:91-120,141-148,167-186): the oracle's restatement
+    against advance(config, scene, xs) of the real reference, several calls so that emitted particles get drained,
+    pulled by the well and queried."""
+    _need(oracle_mod, "strict_stable")
+    from helpers import demo_scene
+    sc = demo_scene()
+    p, xs = oracle_mod.ref_scene_2cubes(2000, 3)
+    a, b = xs.copy(), xs.copy()
+    saw_hit = False
+    for call in range(5):
+        a, answers = oracle_mod.ref_advance_scene(H, p, sc, a, variant="strict_stable", threads=1)
+        b = oracle_mod.scene_edit(H, p, sc, b)
+        t = oracle_mod.step(H, p, b, mode=oracle_mod.GAUSS_SEIDEL, taps=True, scene=sc)
+        assert a.tobytes() == b.tobytes(), f"call {call}: particles differ from the reference"
+        for (qid, ids), first, cnt in zip(answers, t["query_first"], t["query_count"]):
+            assert np.array_equal(ids, b["id"][first:first + cnt]), f"call {call}: query {qid}"
+            saw_hit |= len(ids) > 0
+    assert saw_hit and (b["id"] == 99).sum() > 0 and len(b) != len(xs)  # the scene did something
+
+
 def test_unmodified_reference_via_recovered_permutation(oracle_mod):
     _need(oracle_mod, "strict")
     p, xs = oracle_mod.ref_scene_2cubes(6000, 4)
