@@ -118,7 +118,12 @@ enum {
   PBF_FLAG_STRICT_FP = 1u << 0,    /* no FMA contraction, IEEE div/sqrt in the solver kernels: follows the oracle op-for-op */
   PBF_FLAG_DEBUG_COUNTS = 1u << 1, /* also run the neighbour-count tap each step (PBF_TAP_CAND_COUNT/NBR_COUNT) */
   PBF_FLAG_PROFILE = 1u << 2,      /* record CUDA events around every kernel family (pbf_profile_read) */
-  PBF_FLAG_GLOBAL_NEIGHBOURS = 1u << 3 /* use the one-pass global-memory neighbour kernels (A/B testing) */
+  PBF_FLAG_GLOBAL_NEIGHBOURS = 1u << 3, /* use the one-pass global-memory neighbour kernels (A/B testing) */
+  /* Extensions, default off: NO reference backend has them (sph_constants.h:13-14 only declares C and
+   * VORTICITY_EPSILON; finalise is ompsph.hpp:256-264).  Applied to the velocities after finalise, defined in
+   * csrc/xsph.cu and pinned by oracle/pbf_oracle.c; not available on the slab path. */
+  PBF_FLAG_XSPH = 1u << 4,      /* v_i += C * sum_j (v_j - v_i) poly6(r_ij) */
+  PBF_FLAG_VORTICITY = 1u << 5  /* v_i += dt * VORTICITY_EPSILON * (N x omega_i) */
 };
 
 /* Debug taps, all in SORTED particle order unless stated (pbf_debug_read). */

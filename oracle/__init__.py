@@ -26,6 +26,8 @@ from pbf_sph_b200.capi import PARTICLE, GridInfo, McParams, Params, SceneStruct 
 
 GAUSS_SEIDEL = 1
 SKIP_DIFFUSE = 2
+XSPH = 4       # extension modes: not part of any reference backend
+VORTICITY = 8
 
 
 class OracleIO(C.Structure):

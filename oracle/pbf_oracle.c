@@ -34,6 +34,8 @@
 
 #define PBF_ORACLE_GAUSS_SEIDEL 1u /* in-place delta + in-place diffuse, serial (== reference on 1 thread) */
 #define PBF_ORACLE_SKIP_DIFFUSE 2u
+#define PBF_ORACLE_XSPH 4u      /* extension: XSPH viscosity after finalise (not in any reference backend) */
+#define PBF_ORACLE_VORTICITY 8u /* extension: vorticity confinement after finalise */
 
 /* src/sph_constants.h:5-16 */
 static const float VD = 0.49f;
@@ -44,6 +46,8 @@ static const float CFM_EPSILON = 600.0f;
 static const float CorrDeltaQ = 0.3f;
 static const float CorrK = 0.0001f;
 static const float CorrN = 4.f;
+static const float C_XSPH = 0.00001f;            /* sph_constants.h:13 `C` (declared, never used by the reference) */
+static const float VORTICITY_EPSILON = 0.0005f;  /* sph_constants.h:14 (declared, never used by the reference) */
 
 typedef struct pbf_oracle_io {
   /* optional taps; NULL = not wanted.  All sized by the caller. */
@@ -414,6 +418,85 @@ int pbf_oracle_step(float h, const pbf_params *p, pbf_particle *xs, uint64_t n, 
       pos[3 * a + k] = pstar[3 * a + k] * scale;
       vel[3 * a + k] = (dx * inv_dt + vel[3 * a + k]) * VD;
     }
+
+  /* ---- extension (opt-in; the reference declares the constants but has neither term) ----------------
+   * Macklin & Mueller 2013 §5 on the step's final state: positions pStar (scaled units), the velocities finalise has
+   * just produced, the step's cell table, W = poly6Kernel and grad W = spikyKernelGradient (ompsph.hpp:67-75), sums
+   * in the 27-cell visiting order, Jacobi (all sums read the post-finalise velocities):
+   *   omega_i = (1/RHO) sum_j (v_j - v_i) x grad_{p_j} W(p_i - p_j),   grad_{p_j} W = -spiky(p_i, p_j)
+   *             (1/RHO = the particle volume m/rho_0 at unit mass: the SPH curl estimate)
+   *   eta_i   = sum_j |omega_j| spiky(p_i, p_j),  N = eta / |eta|  (no force when |eta| < EPSILON)
+   *   v_i    += dt * VORTICITY_EPSILON * (N x omega_i)  +  C * sum_j (v_j - v_i) poly6(|p_i - p_j|) */
+  if (mode & (PBF_ORACLE_XSPH | PBF_ORACLE_VORTICITY)) {
+    const int do_x = (mode & PBF_ORACLE_XSPH) != 0, do_v = (mode & PBF_ORACLE_VORTICITY) != 0;
+    float *omega = calloc(4 * n, sizeof(float)), *vnew = malloc(sizeof(float) * 3 * n);
+    if (do_v) {
+#pragma omp parallel for schedule(dynamic, 256)
+      for (int64_t a = 0; a < (int64_t)n; ++a) {
+        uint64_t nk[27];
+        neighbour_keys(key[a], nk);
+        float w[3] = {0.f, 0.f, 0.f};
+        const float *pa = &pstar[3 * a], *va = &vel[3 * a];
+        for (int c = 0; c < 27; ++c) {
+          uint32_t s0, e0;
+          cell_range(table, G, nk[c], &s0, &e0);
+          for (uint32_t b = s0; b < e0; ++b) {
+            const float *pb = &pstar[3 * b];
+            const float r = dist3(pa, pb);
+            if (!spiky_active(r, h)) continue;
+            const float sc = spiky_scalar(r, h, SP);
+            const float g[3] = {-((pa[0] - pb[0]) * sc), -((pa[1] - pb[1]) * sc), -((pa[2] - pb[2]) * sc)};
+            const float d[3] = {vel[3 * b] - va[0], vel[3 * b + 1] - va[1], vel[3 * b + 2] - va[2]};
+            w[0] += d[1] * g[2] - d[2] * g[1];
+            w[1] += d[2] * g[0] - d[0] * g[2];
+            w[2] += d[0] * g[1] - d[1] * g[0];
+          }
+        }
+        for (int k = 0; k < 3; ++k) w[k] *= RHO_RECIP;
+        omega[4 * a] = w[0]; omega[4 * a + 1] = w[1]; omega[4 * a + 2] = w[2];
+        omega[4 * a + 3] = sqrtf((w[0] * w[0] + w[1] * w[1]) + w[2] * w[2]);
+      }
+    }
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t a = 0; a < (int64_t)n; ++a) {
+      uint64_t nk[27];
+      neighbour_keys(key[a], nk);
+      float eta[3] = {0.f, 0.f, 0.f}, xs_sum[3] = {0.f, 0.f, 0.f};
+      const float *pa = &pstar[3 * a], *va = &vel[3 * a];
+      for (int c = 0; c < 27; ++c) {
+        uint32_t s0, e0;
+        cell_range(table, G, nk[c], &s0, &e0);
+        for (uint32_t b = s0; b < e0; ++b) {
+          const float *pb = &pstar[3 * b];
+          const float r = dist3(pa, pb);
+          if (r > h) continue;
+          if (do_x) {
+            const float wgt = poly6(r, P6, h);
+            for (int k = 0; k < 3; ++k) xs_sum[k] += (vel[3 * b + k] - va[k]) * wgt;
+          }
+          if (do_v && r >= EPSILON) {
+            const float sc = spiky_scalar(r, h, SP) * omega[4 * b + 3];
+            for (int k = 0; k < 3; ++k) eta[k] += (pa[k] - pb[k]) * sc;
+          }
+        }
+      }
+      float out[3] = {va[0], va[1], va[2]};
+      if (do_v) {
+        const float len = sqrtf((eta[0] * eta[0] + eta[1] * eta[1]) + eta[2] * eta[2]);
+        if (len >= EPSILON) {
+          const float N[3] = {eta[0] / len, eta[1] / len, eta[2] / len};
+          const float *w = &omega[4 * a];
+          const float f[3] = {N[1] * w[2] - N[2] * w[1], N[2] * w[0] - N[0] * w[2], N[0] * w[1] - N[1] * w[0]};
+          for (int k = 0; k < 3; ++k) out[k] += (dt * VORTICITY_EPSILON) * f[k];
+        }
+      }
+      if (do_x)
+        for (int k = 0; k < 3; ++k) out[k] += C_XSPH * xs_sum[k];
+      for (int k = 0; k < 3; ++k) vnew[3 * a + k] = out[k];
+    }
+    memcpy(vel, vnew, sizeof(float) * 3 * n);
+    free(omega); free(vnew);
+  }
 
   /* ---- marching cubes: ompsph.hpp:277-477 ---- */
   if (p->surface_enabled) {

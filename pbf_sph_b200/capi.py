@@ -26,6 +26,8 @@ FLAG_STRICT_FP = 1 << 0
 FLAG_DEBUG_COUNTS = 1 << 1
 FLAG_PROFILE = 1 << 2
 FLAG_GLOBAL_NEIGHBOURS = 1 << 3
+FLAG_XSPH = 1 << 4       # extensions, default off (no reference backend has them)
+FLAG_VORTICITY = 1 << 5
 
 TAP_KEYS_INPUT, TAP_PERM, TAP_KEYS_SORTED, TAP_CELL_TABLE, TAP_CAND_COUNT, TAP_NBR_COUNT = range(6)
 TAP_LAMBDA, TAP_RHO, TAP_IDS, TAP_MC_FIELD, TAP_MC_COLOUR = range(6, 11)

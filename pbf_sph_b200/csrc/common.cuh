@@ -326,6 +326,9 @@ int solver_delta(pbf_ctx *ctx, uint32_t first, uint32_t count, const float4 *pst
 int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *col_in,
                          float4 *col_out);
 int launch_finalise(pbf_ctx *ctx, const float4 *pstar, float4 *pos, float4 *vel);
+// opt-in extension after finalise (xsph.cu): XSPH viscosity / vorticity confinement per ctx->flags
+int launch_xsph_vorticity(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *pstar, float4 *vel,
+                          float4 *scratch_omega, float4 *scratch_vel);
 int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *total_out_dev);
 int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col);
 

@@ -219,6 +219,9 @@ static int step_device(pbf_ctx *ctx, const pbf_params &p) {
   }
   PBF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   PBF_TRY(launch_finalise(ctx, ctx->pstar[0].p, ctx->pos[ctx->cur].p, ctx->vel[ctx->cur].p));
+  // opt-in extension (no reference backend has it): scratch = the spare position / velocity set of the reorder
+  PBF_TRY(launch_xsph_vorticity(ctx, ctx->keys_sorted, ctx->table.p, ctx->pstar[0].p, ctx->vel[ctx->cur].p,
+                                ctx->pos[ctx->cur ^ 1].p, ctx->vel[ctx->cur ^ 1].p));
   ctx->n_triangles = 0;
   ctx->mc_valid = false;
   if (p.surface_enabled)

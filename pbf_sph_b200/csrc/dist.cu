@@ -969,8 +969,11 @@ int pbf_dist_step(pbf_ctx *ctx, const pbf_params *params) {
   if (!params) return fail(ctx, PBF_ERR_INVALID, "params", "NULL");
   if (!(params->scale > 0.f) || !(params->dt > 0.f)) return fail(ctx, PBF_ERR_INVALID, "params", "scale and dt must be > 0");
   std::vector<pbf_ctx *> &L = *ctx->dist->group;
-  for (pbf_ctx *c : L)
+  for (pbf_ctx *c : L) {
     if (!c->have_state) return fail(ctx, PBF_ERR_STATE, "pbf_dist_step", "pbf_dist_upload on every rank first");
+    if ((c->flags & (PBF_FLAG_XSPH | PBF_FLAG_VORTICITY)) || !c->scene.empty())
+      return fail(ctx, PBF_ERR_STATE, "pbf_dist_step", "scene dynamics and the XSPH/vorticity extensions are single-device only");
+  }
   const int rc = group_step(L, *params);
   if (rc != PBF_OK && ctx->err.empty())
     for (pbf_ctx *c : L)

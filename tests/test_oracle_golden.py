@@ -117,3 +117,26 @@ def test_cell_table_invariants(oracle_mod):
     assert np.array_equal(np.diff(table), counts[:-1])
     assert np.array_equal(np.sort(t["perm"]), np.arange(len(xs)))
     assert t["cand_count"].max() <= 343 and t["nbr_count"].min() >= 1  # self is always in radius
+
+
+def test_extension_modes_are_opt_in_and_well_behaved(oracle_mod):
+    """XSPH / vorticity (oracle modes; no reference backend has them): off by default, velocities only,
+    XSPH conserves momentum and damps relative motion, vorticity confinement is a small correction."""
+    from pbf_sph_b200 import scenes
+    p, xs = scenes.two_cubes(4000, 3)
+    for f in range(15):
+        oracle_mod.step(H, scenes.apply_motion(p, f), xs)
+    pf = scenes.apply_motion(p, 15)
+    out = {}
+    for name, mode in (("plain", 0), ("xsph", oracle_mod.XSPH), ("vort", oracle_mod.VORTICITY)):
+        a = xs.copy()
+        oracle_mod.step(H, pf, a, mode=mode)
+        out[name] = a
+    for name in ("xsph", "vort"):
+        assert np.array_equal(out[name]["position"], out["plain"]["position"])
+        assert not np.array_equal(out[name]["velocity"], out["plain"]["velocity"])
+    v0, vx, vv = (out[k]["velocity"].astype(np.float64) for k in ("plain", "xsph", "vort"))
+    assert np.allclose(v0.sum(0), vx.sum(0), rtol=0, atol=1e-5 * np.abs(v0).sum(0).max())
+    ke = lambda v: 0.5 * ((v - v.mean(0)) ** 2).sum()
+    assert ke(vx) < ke(v0)
+    assert np.abs(vv - v0).max() < 0.05 * np.abs(v0).max()
