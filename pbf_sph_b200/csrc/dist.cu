@@ -123,6 +123,7 @@ struct pbf_dist_state {
   // device scratch
   DevBuf<uint32_t> d_splits, d_row, d_all, d_hist;
   DevBuf<uint32_t> mask, send_idx, blk_cnt, k2, v2, keys_local, role, sub_cnt;
+  bool diffuse_pending = false;  // colour diffusion of this step is still running on the side stream
   DevBuf<float4> sb_a, sb_b, sb_c;
   DevBuf<unsigned long long> sb_id;
   DevBuf<uint32_t> sb_key;
@@ -786,7 +787,17 @@ int phase_e(pbf_ctx *c) {
     PBF_TRY(launch_neighbour_counts(c, c->keys_sorted, c->table.p, c->pstar[0].p, c->cand_count.p, c->nbr_count.p));
   }
   PBF_CUDA(c, c->col[c->cur_col ^ 1].reserve(d->n_local + 1));
-  PBF_TRY(launch_diffuse_tiled(c, c->keys_sorted, c->table.p, c->col[c->cur_col].p, c->col[c->cur_col ^ 1].p));
+  {  // colour diffusion beside the solver iterations (as in the single-device step); group_step joins before finalise
+    PBF_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+    PBF_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->side_stream;
+    const int rc = launch_diffuse_tiled(c, c->keys_sorted, c->table.p, c->col[c->cur_col].p, c->col[c->cur_col ^ 1].p);
+    c->stream = main_stream;
+    PBF_TRY(rc);
+    PBF_CUDA(c, cudaEventRecord(c->ev_join, c->side_stream));
+    d->diffuse_pending = true;
+  }
   c->cur_col ^= 1;
   return PBF_OK;
 }
@@ -863,6 +874,10 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
   for (pbf_ctx *c : L) {
     D *d = c->dist;
     PBF_CUDA(c, cudaSetDevice(c->device));
+    if (d->diffuse_pending) {
+      PBF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+      d->diffuse_pending = false;
+    }
     if (d->n_own) {
       c->sc.n = d->n_own;
       PBF_TRY(launch_finalise(c, c->pstar[0].p + d->own_off, c->pos[c->cur].p + d->own_off, c->vel[c->cur].p + d->own_off));
