@@ -159,6 +159,10 @@ def workload(name: str, world: int):
     if name == "dam-1m":
         p, xs = scenes.dam_break(100, 4)
         return name, "dam-break 100^3 = 1 000 000 particles, 4 solver iterations, no surface extraction", p, xs
+    if name == "dam-1m-mc":  # BASELINE.json configs[3]: the mesh-generation path
+        p, xs = scenes.dam_break(100, 4)
+        p.surface_enabled = 1
+        return name, "dam-break 100^3 = 1 000 000 particles, 4 solver iterations, marching-cubes surface every step", p, xs
     if name == "dam-64k":
         p, xs = scenes.dam_break(40, 4)
         return name, "dam-break 40^3 = 64 000 particles, 4 solver iterations", p, xs

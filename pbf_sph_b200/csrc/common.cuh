@@ -73,6 +73,7 @@ struct McConst {
   float resolution, isolevel, particle_size, particle_influence;
   float step;       // h / resolution
   float threshold;  // h * scale
+  float r2_hit;     // largest squared distance whose glm::fastSqrt is < threshold (mc.cu)
   uint32_t sample[3];
   uint32_t march[3];
   uint64_t lattice_n, march_n;

@@ -6,6 +6,9 @@
 // The reference hands out triangle slots with a global atomic counter (order depends on thread timing); the scan
 // makes the order deterministic: ascending cube index, which is also what one reference thread produces.
 // It uses the post-finalise positions with the cell table built before the solve (stale grid), as the reference does.
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
 #include "pbf/mc_tables.h"
 
@@ -21,16 +24,31 @@ __constant__ int c_edge[12][2] = PBF_MC_EDGE_CORNERS_INIT;
 
 __device__ __forceinline__ float glm_fast_sqrt(float x) { return fdiv(1.0f, fdiv(1.0f, fsqrt(x))); }  // gtx/fast_square_root
 
+// Lattice points are taken in 4 x 4 x 8 tiles (x, y, z), one tile per 128-thread block, so that a warp's 32 points
+// (4 in y, 8 in z, one x) span only 2 x 4 cells at the stock resolution of 2: similar candidate counts in every lane
+// and neighbouring table / particle reads.  Each point works in two phases like the solver's neighbour list:
+//   1. the 27-cell walk tests every candidate on the squared distance only and appends the hits to the thread's list
+//      in shared memory.  The reference tests  glm::fastSqrt(r2) < threshold  (fastSqrt = 1 / (1 / sqrt)): that map is
+//      monotone in r2, so the host finds the largest r2 that passes (McConst::r2_hit) and the test is one compare;
+//   2. the expensive part (two IEEE divides and a sqrt for the distance, powf, four divides, the colour gather) runs
+//      over the hits only, every lane busy, in the order they were found — so every sum is the reference's sum.
+// ncu on the one-phase form: 1.68 G warp instructions at 12 of 32 lanes, 90 % issue-bound, the hit code at 5 lanes.
+constexpr int kFieldCap = 48;    // hits a point can hold; a full list is evaluated on the spot (rare: one lane works)
+constexpr int kFieldFlush = 32;  // after each cell: if ANY lane holds this many, the whole warp evaluates its lists
+
 __global__ void __launch_bounds__(kMcBlock) mc_field_kernel(StepConst c, McConst m, const uint32_t *__restrict__ table,
                                                             const float4 *__restrict__ pos,
                                                             const float4 *__restrict__ col, float4 *__restrict__ PN,
                                                             float4 *__restrict__ LC) {
-  const uint64_t idx = (uint64_t)blockIdx.x * kMcBlock + threadIdx.x;
-  if (idx >= m.lattice_n) return;
-  const uint32_t sy = m.sample[1], sz = m.sample[2];
-  const uint32_t x = (uint32_t)(idx / ((uint64_t)sy * sz));
-  const uint32_t y = (uint32_t)((idx - (uint64_t)x * sy * sz) / sz);
-  const uint32_t z = (uint32_t)(idx - (uint64_t)x * sy * sz - (uint64_t)y * sz);
+  __shared__ uint32_t s_list[kFieldCap * kMcBlock];  // [slot][thread]: conflict-free
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ntz = (m.sample[2] + 7u) / 8u, nty = (m.sample[1] + 3u) / 4u;
+  const uint32_t bz = blockIdx.x % ntz, by = (blockIdx.x / ntz) % nty, bx = blockIdx.x / (ntz * nty);
+  const uint32_t x = bx * 4u + (tid >> 5), y = by * 4u + ((tid >> 3) & 3u), z = bz * 8u + (tid & 7u);
+  // no early exit: every lane walks the 27 cells (lanes without a lattice point see empty cells), so the warp is
+  // converged at the end of each cell and can decide together when to evaluate
+  bool alive = x < m.sample[0] && y < m.sample[1] && z < m.sample[2];
+  const uint64_t idx = ((uint64_t)x * m.sample[1] + y) * m.sample[2] + z;  // index3d, curves.h:17-19
   const float lp[3] = {(float)x, (float)y, (float)z};
   float a[3];
   int c0[3];
@@ -39,10 +57,10 @@ __global__ void __launch_bounds__(kMcBlock) mc_field_kernel(StepConst c, McConst
     a[k] = fmul(fadd(c.min_extent[k], fmul(lp[k], m.step)), c.scale);                       // ompsph.hpp:291
     c0[k] = (int)compact10(spread10(cell_coord(fdiv(lp[k], m.resolution))));                // ompsph.hpp:294-299
   }
-  if ((uint32_t)c0[0] == c.extent[0] && (uint32_t)c0[1] == c.extent[1] && (uint32_t)c0[2] == c.extent[2]) {
+  if (alive && (uint32_t)c0[0] == c.extent[0] && (uint32_t)c0[1] == c.extent[1] && (uint32_t)c0[2] == c.extent[2]) {
     PN[idx] = make_float4(0.f, 0.f, 0.f, 0.f);  // ompsph.hpp:301-304: the entry keeps its zero initialisation
     LC[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
+    alive = false;
   }
   int nb[3][3];
 #pragma unroll
@@ -54,8 +72,30 @@ __global__ void __launch_bounds__(kMcBlock) mc_field_kernel(StepConst c, McConst
   }
   float v = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
   float cx = 0.f, cy = 0.f, cz = 0.f, cw = 0.f;
-  uint32_t nn = 0;
+  uint32_t nn = 0, held = 0;
   const float w = fmul(-m.particle_influence, m.particle_size);
+  const bool half_power = m.particle_influence == 0.5f;
+  uint32_t *mine = s_list + tid;
+  auto evaluate = [&]() {  // the sums of ompsph.hpp:329-345 over the held hits, in the order they were found
+    for (uint32_t i = 0; i < held; ++i) {
+      const uint32_t b = mine[i * kMcBlock];
+      const float4 pb = ldg4(pos + b);
+      const float ex = fsub(a[0], pb.x), ey = fsub(a[1], pb.y), ez = fsub(a[2], pb.z);
+      const float d = glm_fast_sqrt(fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(ez, ez)));
+      const float lx = fsub(pb.x, a[0]), ly = fsub(pb.y, a[1]), lz = fsub(pb.z, a[2]);
+      // glm::pow(len, influence); |l| == d bit for bit (squares of negated terms).  The stock influence is 0.5, where
+      // the correctly rounded square root is at least as close to glibc's powf as CUDA's powf is (both <= 1 ulp)
+      const float den = half_power ? fsqrt(d) : powf(d, m.particle_influence);
+      v = fadd(v, fdiv(m.particle_size, den));
+      nx = fadd(nx, fmul(w, fdiv(lx, den)));
+      ny = fadd(ny, fmul(w, fdiv(ly, den)));
+      nz = fadd(nz, fmul(w, fdiv(lz, den)));
+      const float4 cb = ldg4(col + b);
+      cx = fadd(cx, cb.x); cy = fadd(cy, cb.y); cz = fadd(cz, cb.z); cw = fadd(cw, cb.w);
+    }
+    nn += held;
+    held = 0;
+  };
 #pragma unroll 1
   for (int kz = 0; kz < 3; ++kz)
 #pragma unroll 1
@@ -63,26 +103,28 @@ __global__ void __launch_bounds__(kMcBlock) mc_field_kernel(StepConst c, McConst
 #pragma unroll 1
       for (int kx = 0; kx < 3; ++kx) {  // order of ompsph.hpp:313-326
         const uint32_t o = morton3((uint32_t)nb[0][kx], (uint32_t)nb[1][ky], (uint32_t)nb[2][kz]);
-        if (o >= c.G) continue;
-        const uint32_t s = __ldg(table + o);
-        const uint32_t e = (o + 1 < c.G) ? __ldg(table + o + 1) : s;
-        for (uint32_t b = s; b < e; ++b) {
-          const float4 pb = ldg4(pos + b);
-          const float ex = fsub(a[0], pb.x), ey = fsub(a[1], pb.y), ez = fsub(a[2], pb.z);
-          const float d = glm_fast_sqrt(fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(ez, ez)));
-          if (d < m.threshold) {
-            const float lx = fsub(pb.x, a[0]), ly = fsub(pb.y, a[1]), lz = fsub(pb.z, a[2]);
-            const float den = powf(d, m.particle_influence);  // |l| == d bit for bit (squares of negated terms)
-            v = fadd(v, fdiv(m.particle_size, den));
-            nx = fadd(nx, fmul(w, fdiv(lx, den)));
-            ny = fadd(ny, fmul(w, fdiv(ly, den)));
-            nz = fadd(nz, fmul(w, fdiv(lz, den)));
-            const float4 cb = ldg4(col + b);
-            cx = fadd(cx, cb.x); cy = fadd(cy, cb.y); cz = fadd(cz, cb.z); cw = fadd(cw, cb.w);
-            ++nn;
+        uint32_t s = 0, e = 0;
+        if (alive && o < c.G) {
+          s = __ldg(table + o);
+          e = (o + 1 < c.G) ? __ldg(table + o + 1) : s;
+        }
+        for (uint32_t b = s; b < e; b += 4u) {  // four positions in flight per lane
+          float4 pb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pb[u] = ldg4(pos + min(b + u, e - 1u));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float ex = fsub(a[0], pb[u].x), ey = fsub(a[1], pb[u].y), ez = fsub(a[2], pb[u].z);
+            if (b + u < e && fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(ez, ez)) <= m.r2_hit) {  // fastSqrt(r2) < threshold
+              mine[held * kMcBlock] = b + u;
+              if (++held == kFieldCap) evaluate();
+            }
           }
         }
+        if (__any_sync(0xFFFFFFFFu, held >= kFieldFlush)) evaluate();
       }
+  evaluate();
+  if (!alive) return;
   const float inv = fdiv(1.0f, fsqrt(fadd(fadd(fmul(nx, nx), fmul(ny, ny)), fmul(nz, nz))));  // fastNormalize
   PN[idx] = make_float4(v, fmul(nx, inv), fmul(ny, inv), fmul(nz, inv));
   const float fn = (float)nn;
@@ -174,6 +216,21 @@ int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float
   m.particle_influence = p.surface.particle_influence;
   m.step = ctx->h / p.surface.resolution;  // ompsph.hpp:290
   m.threshold = ctx->h * p.scale * 1;      // ompsph.hpp:292
+  {  // largest r2 with glm::fastSqrt(r2) < threshold (fastSqrt = 1 / (1 / sqrt(x)) is monotone): bisection on the bits
+    auto passes = [&](float x) { return 1.0f / (1.0f / std::sqrt(x)) < m.threshold; };
+    uint32_t lo = 0u, hi = 0x7f7fffffu;  // passes(lo) holds for threshold > 0; find the last bit pattern that passes
+    m.r2_hit = -1.0f;                     // nothing passes (threshold <= 0)
+    float f;
+    std::memcpy(&f, &lo, 4);
+    if (passes(f)) {
+      while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo + 1u) / 2u;
+        std::memcpy(&f, &mid, 4);
+        if (passes(f)) lo = mid; else hi = mid - 1u;
+      }
+      std::memcpy(&m.r2_hit, &lo, 4);
+    }
+  }
   for (int a = 0; a < 3; ++a) {
     m.sample[a] = ctx->grid.sample_size[a];
     m.march[a] = m.sample[a] - 1;
@@ -187,8 +244,9 @@ int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float
   PBF_CUDA(ctx, ctx->mc_offset.reserve(m.march_n + 1));
   {
     PhaseScope ps(ctx, PBF_PH_MC_FIELD);
-    mc_field_kernel<<<div_up(m.lattice_n, kMcBlock), kMcBlock, 0, ctx->stream>>>(ctx->sc, m, table, pos, col,
-                                                                                ctx->mc_pn.p, ctx->mc_c.p);
+    const uint64_t tiles = (uint64_t)((m.sample[0] + 3u) / 4u) * ((m.sample[1] + 3u) / 4u) * ((m.sample[2] + 7u) / 8u);
+    if (tiles >= (1ull << 31)) return fail(ctx, PBF_ERR_INVALID, "surface", "lattice too large");
+    mc_field_kernel<<<(unsigned)tiles, kMcBlock, 0, ctx->stream>>>(ctx->sc, m, table, pos, col, ctx->mc_pn.p, ctx->mc_c.p);
     PBF_LAUNCH_CHECK(ctx);
   }
   ctx->mc_valid = true;
