@@ -279,7 +279,7 @@ def run_single(args):
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     stream = torch.cuda.Stream()
-    s = Solver(scenes.H, dev, FLAG_PROFILE | args.flags)
+    s = Solver(scenes.H, dev, args.flags)
     s.set_stream(stream.cuda_stream)
     s.upload(xs)
     # settle the fluid first (throughput depends on the state: ~266 candidates/particle on the initial lattice,
@@ -301,10 +301,25 @@ def run_single(args):
         torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     launches = s.launch_count() - l0
-    prof = s.profile()
     value = n * iters * args.steps / (ms_total * 1e-3)
+    # the same K steps again with the library's per-family CUDA events on (PBF_FLAG_PROFILE: ~30 event records per
+    # step, ~2 % of the step, which is why `value` above is timed without them): the roofline's launch durations
+    s.set_flags(FLAG_PROFILE | args.flags)
+    s.profile_reset()
+    torch.cuda.synchronize()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        s.step(p)
+    e3.record(stream)
+    torch.cuda.synchronize()
+    ms_profiled = e2.elapsed_time(e3)
+    prof = s.profile()
+    s.set_flags(args.flags)
 
     roofline = roofline_of(prof, n, iters, args.steps)
+    roofline["region"] = (f"{args.steps} further steps with per-family CUDA events recorded by the library on its stream "
+                          f"({ms_profiled / args.steps:.4f} ms/step with events, {ms_total / args.steps:.4f} without)")
 
     # end to end through the drop-in call, pinned host buffers
     snap = s.download()

@@ -139,7 +139,7 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
     if rank == 0:
         idt.copy_(torch.frombuffer(bytearray(SlabRank.unique_id()), dtype=torch.uint8))
     dist.broadcast(idt, 0)
-    sr = SlabRank(scenes.H, local, rank, world, bytes(idt.cpu().numpy().tobytes()), capi.FLAG_PROFILE | args.flags)
+    sr = SlabRank(scenes.H, local, rank, world, bytes(idt.cpu().numpy().tobytes()), args.flags)
     stream = torch.cuda.Stream()
     sr.s.set_stream(stream.cuda_stream)
     mine = shard(xs, rank, world)
@@ -164,7 +164,18 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = sr.s.launch_count() - l0
+    # the same steps again with the library's per-family CUDA events on (they cost ~2 % of a step, so `value` is
+    # timed without them): per-rank phase times and the roofline's launch durations
+    sr.s.set_flags(capi.FLAG_PROFILE | args.flags)
+    sr.s.profile_reset()
+    torch.cuda.synchronize()
+    dist.barrier()
+    for _ in range(args.steps):
+        sr.step(p)
+    torch.cuda.synchronize()
+    dist.barrier()
     prof = sr.s.profile()
+    sr.s.set_flags(args.flags)
     st = sr.stats()
 
     # end to end: every step uploads the rank's particles from pinned host memory and reads them back into it
