@@ -65,8 +65,9 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period: float = 0.02, enabled: bool = True):
         self.index, self.rows, self.proc, self.stop, self.how = index, [], None, threading.Event(), None
+        self.period, self.enabled = period, enabled
 
     def _nvml_loop(self, nv, h, mx):
         bits = [getattr(nv, n, 0) for n in ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksEventReasonHwThermalSlowdown",
@@ -84,10 +85,12 @@ class ClockSampler:
                 self.rows.append([str(sm), str(mx)] + ["Active" if (b and r & b) else "Not Active" for b in bits])
             except Exception:
                 pass
-            if self.stop.wait(0.02):
+            if self.stop.wait(self.period):
                 break
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -293,7 +296,7 @@ def run_single(args):
     l0 = s.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    with ClockSampler(dev) as clk:
+    with ClockSampler(dev, period=0.05) as clk:
         e0.record(stream)
         for _ in range(args.steps):
             s.step(p)

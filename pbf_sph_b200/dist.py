@@ -153,7 +153,8 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     dist.barrier()
-    with ClockSampler(local) as clk:
+    # NVML queries go through the driver: one sampler (rank 0, 10 Hz) is enough and keeps the other ranks' launches quiet
+    with ClockSampler(local, period=0.1, enabled=(rank == 0)) as clk:
         e0.record(stream)
         for _ in range(args.steps):
             sr.step(p)
