@@ -1,26 +1,33 @@
-// cell_search.cu — the neighbour search of one solver iteration, one WARP PER OCCUPIED CELL.
+// cell_search.cu — the neighbour search of one solver iteration with one WARP PER OCCUPIED CELL (PBF_SEARCH=cells).
 //
-// The thread-per-particle search (neighbour_list.cu, lambda_list_kernel phase 1) is bound by the L1 data pipe and by
-// divergence, not by arithmetic: every lane walks its own 18 runs (17.8 of 32 lanes active on average), and every
-// candidate costs each lane one 128-bit gather (4-5 L1 wavefronts per warp instruction; ncu r01b: l1tex data-pipe
-// wavefronts 75 % of peak).  All particles of one cell share the same 27 neighbour cells (sph.hpp:215-236), so here
+// An alternative to the production search (neighbour_list.cu, lambda_list_kernel phase 1: one thread per particle walks
+// the cell table; ncu: 17.8 of 32 lanes active, because the lanes of a warp sit in ~5 different cells whose 18 runs all
+// differ in length).  All particles of one cell share the same 27 neighbour cells (sph.hpp:215-236), so here
 //
+//   once per step (keys and cell table are fixed for all iterations, ompsph.hpp:215-249) — cell_plan_kernel:
 //   * a warp takes the cells whose first particle lies in its 32-particle window of the Z-sorted array;
-//   * lanes 0..26 look up the 27 cell ranges (one table access each) and a warp scan turns them into ONE flat
-//     candidate sequence in the reference's visiting order (x fastest, then y, then z; ascending index in a cell);
-//   * the candidates are loaded ONCE per cell, 32 at a time, coalesced (lane j holds candidate j), up to 8 chunks
-//     (256 candidates) in registers, two chunks per 64-bit register pair;
+//   * lanes 0..26 look up the 27 cell ranges (one table access each), a warp scan flattens them into ONE candidate
+//     sequence in the reference's visiting order (x fastest, then y, then z; ascending index in a cell), and the
+//     sequence is written out as the cell's candidate list;
+//
+//   once per iteration — search_cells_kernel:
+//   * the cell's candidates are loaded ONCE, 32 at a time, coalesced (lane j holds candidate j), up to 8 chunks
+//     (256 candidates) in registers, two chunks per 64-bit register pair; the next cell's list is already in flight;
 //   * the cell's particles ("targets") are then taken one by one: every lane tests ITS candidates against the
 //     target — two candidates per instruction with Blackwell's packed FADD2/FMUL2/FFMA2 — a ballot gives the hit
 //     mask of the chunk, and the hit lanes append their candidate's index to the target's list at
 //     count + popc(mask below me): the list is in visiting order, exactly the list the thread-per-particle search
-//     writes, so the sums formed from it are bit-identical.
+//     writes, so the sums formed from it are bit-identical (tests/test_parity_gpu.py).
 //
-// No lane ever idles on another lane's run and no candidate is loaded more than once per cell.  The list layout
-// (nl[k * stride + particle], n_hits[particle]) is the one lambda_sums / delta_list read (neighbour_list.cu).  Hits are
-// staged in shared memory, eight targets at a time, and written out as 32-byte row segments: a hit lane's own global
-// store would cost one L1 wavefront per hit (28 M per iteration at 1 M particles).  A particle with more than kCap hits
-// is flagged by n_hits > kCap and its sums take the one-pass walk.
+// No lane idles on another lane's run (31.5 of 32 active) and no candidate is loaded more than once per cell.  Hits are
+// staged in shared memory, eight targets at a time, and written out as 32-byte row segments into the list layout
+// lambda_sums / delta_list read (nl[k * stride + particle], n_hits[particle]); a particle with more than kCap hits is
+// flagged by n_hits > kCap and its sums take the one-pass walk.
+//
+// MEASURED SLOWER than the production search (dam-1m: 320 us + 79 us for the sums against 340 us fused; lambda 1.50
+// against 1.32 ms/step): the ballot/popc/append bookkeeping costs as many instructions per pair as the divergence it
+// removes, and the per-cell load chain runs at 17-24 warps/SM.  Kept as an A/B option; profiles/r01c_search_experiments.txt
+// has the ncu figures of every stage of this kernel.
 #include "cells.cuh"
 #include "common.cuh"
 #include "pair_math.cuh"
