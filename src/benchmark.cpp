@@ -34,7 +34,7 @@ using Params = sph::SphParams<size_t, float, pbf::vec>;
 using Result = sph::Result<size_t, float, pbf::vec>;
 
 struct Options {
-  std::string impl = "cuda", output = "./out_{impl}_{type}_{iter}", scene = "2cubes", device = "0";
+  std::string impl = "cuda", output = "./out_{impl}_{type}_{iter}", scene = "2cubes", device = "0", saveState, loadState;
   size_t iterations = 200, warmup = 200, particles = 20000, solverIter = 6;
   bool list = false, verbose = false, fp64 = false, surface = true, resident = false, fountain = false, help = false;
 };
@@ -53,6 +53,8 @@ static void usage() {
                "                              {iter}, {impl}, {type}. Default: ./out_{impl}_{type}_{iter}\n"
                "      --scene=[2cubes|dam]    Stock two-cube scene with the moving wall, or a dam-break block\n"
                "      --particles=[N]         Particle budget of the scene. Default: 20000\n"
+               "      --save-state=[FILE]     Checkpoint: write the final particles (raw 56-byte sph::Particle records) to FILE\n"
+               "      --load-state=[FILE]     Resume: start from the particles of a checkpoint instead of the scene's\n"
                "      --fountain              Pass a non-empty sph::Scene to every advance(): a well, a source, a drain and\n"
                "                              two queries (the scene of tests/helpers.py demo_scene)\n"
                "      --solver-iters=[I]      Solver iterations per step. Default: 6\n"
@@ -91,6 +93,8 @@ static Options parse(int argc, char **argv) {
     else if (take(argc, argv, i, "w", "warmup", v)) o.warmup = std::stoull(v);
     else if (take(argc, argv, i, "o", "output", v)) o.output = v;
     else if (take(argc, argv, i, nullptr, "scene", v)) o.scene = v;
+    else if (take(argc, argv, i, nullptr, "save-state", v)) o.saveState = v;
+    else if (take(argc, argv, i, nullptr, "load-state", v)) o.loadState = v;
     else if (take(argc, argv, i, nullptr, "particles", v)) o.particles = std::stoull(v);
     else if (take(argc, argv, i, nullptr, "solver-iters", v)) o.solverIter = std::stoull(v);
     else if (take(argc, argv, i, nullptr, "surface", v)) o.surface = (v == "on" || v == "1" || v == "true");
@@ -102,6 +106,28 @@ static Options parse(int argc, char **argv) {
 static std::string replaceAll(std::string s, const std::string &from, const std::string &to) {
   for (size_t p = 0; (p = s.find(from, p)) != std::string::npos; p += to.size()) s.replace(p, from.size(), to);
   return s;
+}
+
+// Checkpoint / resume: "PBFSTATE", u64 count, then the particles exactly as they cross advance() (56-byte records).
+static void saveState(const std::vector<Particle> &xs, const std::string &file) {
+  std::ofstream out(file, std::ios::binary);
+  const uint64_t n = xs.size();
+  out.write("PBFSTATE", 8);
+  out.write(reinterpret_cast<const char *>(&n), sizeof(n));
+  out.write(reinterpret_cast<const char *>(xs.data()), std::streamsize(n * sizeof(Particle)));
+  if (!out) throw std::runtime_error("cannot write " + file);
+}
+static std::vector<Particle> loadState(const std::string &file) {
+  std::ifstream in(file, std::ios::binary);
+  char magic[8];
+  uint64_t n = 0;
+  in.read(magic, 8);
+  in.read(reinterpret_cast<char *>(&n), sizeof(n));
+  if (!in || std::string(magic, 8) != "PBFSTATE") throw std::runtime_error(file + " is not a particle checkpoint");
+  std::vector<Particle> xs(n);
+  in.read(reinterpret_cast<char *>(xs.data()), std::streamsize(n * sizeof(Particle)));
+  if (!in) throw std::runtime_error(file + " is truncated");
+  return xs;
 }
 
 static void save(const Result &result, const std::vector<Particle> &xs, const std::string &dir) {
@@ -157,6 +183,7 @@ int main(int argc, char *argv[]) {
         ? sph::damBreak<size_t, float, pbf::vec>(static_cast<size_t>(std::cbrt(double(o.particles)) + 0.5), o.solverIter, scaling)
         : sph::simpleConfigWith2Cubes<size_t, float, pbf::vec>(o.particles, o.solverIter, scaling);
     if (o.surface) param.surface = mc;  // marching cubes is ON in the stock benchmark (benchmark.cpp:29)
+    if (!o.loadState.empty()) particles = loadState(o.loadState);
     const bool moving = o.scene != "dam";
     if (o.verbose) std::cout << "scene=" << o.scene << " particles=" << particles.size() << " solver-iters=" << o.solverIter
                              << " surface=" << (o.surface ? "on" : "off") << " resident=" << o.resident << std::endl;
@@ -225,6 +252,7 @@ int main(int argc, char *argv[]) {
               << "Query answers        :" << [&] { std::string q; for (const auto &a : result.queries) q += " " + std::to_string(a.id) + ":" + std::to_string(a.neighbours.size()); return q.empty() ? std::string(" none") : q; }() << "\n"
               << "Particle-iterations/s: " << double(particles.size()) * double(o.solverIter) * double(o.iterations) / seconds << "\n"
               << std::endl;
+    if (!o.saveState.empty()) saveState(particles, o.saveState);
     save(result, particles, output);
     std::cout << "Results flushed." << std::endl;
   } catch (const std::exception &e) {

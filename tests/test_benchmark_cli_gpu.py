@@ -74,3 +74,19 @@ def test_benchmark_with_a_scene_matches_python_mirror(gpu, tmp_path):
     rec = np.frombuffer(body, dtype=np.dtype([("xyz", "<f4", 3), ("rgba", "<f4", 4), ("id", "<u4")]))
     assert np.array_equal(rec["id"], xs["id"].astype(np.uint32)) and np.array_equal(rec["xyz"], xs["position"])
     assert run("--fountain", "--resident", "-n1", "-w0", "-o", "").returncode != 0
+
+
+def test_checkpoint_resume_is_bit_exact(gpu, tmp_path):
+    """--save-state / --load-state: 3 + 3 frames through a checkpoint file equal 6 frames in one go, bit for bit (the
+    step is deterministic and the checkpoint holds exactly what crosses advance())."""
+    common = ["--scene=dam", "--particles=27000", "--solver-iters=3", "--surface=off", "-w", "0"]
+    assert run(*common, "-n", "6", "--save-state", str(tmp_path / "six.bin"), "-o", "").returncode == 0
+    assert run(*common, "-n", "3", "--save-state", str(tmp_path / "three.bin"), "-o", "").returncode == 0
+    out = run(*common, "-n", "3", "--load-state", str(tmp_path / "three.bin"), "--save-state", str(tmp_path / "resumed.bin"), "-o", "")
+    assert out.returncode == 0 and "Final Particle count : 27000" in out.stdout
+    six, resumed = (tmp_path / "six.bin").read_bytes(), (tmp_path / "resumed.bin").read_bytes()
+    assert six[:8] == b"PBFSTATE" and len(six) == 16 + 27000 * 56
+    assert six == resumed
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"nonsense")
+    assert run(*common, "-n", "1", "--load-state", str(bad), "-o", "").returncode != 0
