@@ -416,6 +416,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # launched by hand without torchrun: re-launch one rank per GPU the way the driver does
+        os.dup2(sys.stdout.fileno(), 1)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
+                                   str(Path(__file__).resolve())] + sys.argv[1:])
     if args.impl == "reference":
         run_reference(args)
     elif args.gpus <= 1 and int(os.environ.get("WORLD_SIZE", "1")) <= 1:
