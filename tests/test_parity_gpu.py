@@ -218,3 +218,36 @@ def test_dam_break_parity_and_full_size_properties(gpu, oracle_mod):
     assert np.array_equal(np.sort(out["id"]), np.arange(len(xs), dtype=np.uint64)), "ids are conserved"
     lo, hi = np.array(p.min_bound[:]), np.array(p.max_bound[:])
     assert np.all(out["position"] >= lo - 1e-3) and np.all(out["position"] <= hi + 1e-3), "clamped to the box"
+
+
+@pytest.mark.parametrize("seed,n,flags", [(1, 5000, FLAG_STRICT_FP), (2, 12345, 0), (3, 777, FLAG_STRICT_FP), (4, 40000, 0)])
+def test_random_clouds(gpu, oracle_mod, monkeypatch, seed, n, flags):
+    """Not a lattice: uniformly random positions in a slab of the box, random velocities (some fast enough to leave the
+    padded grid), random masses and colours, ids in random order.  Integer artefacts bit-exact, lambda and the step
+    within the float tolerance, for both neighbour searches."""
+    rng = np.random.default_rng(seed)
+    p, _ = scenes.two_cubes(2000, 3)
+    xs = np.zeros(n, capi.PARTICLE)
+    xs["id"] = rng.permutation(n).astype(np.uint64)
+    xs["mass"] = rng.uniform(0.5, 1.5, n).astype(np.float32)
+    side = 1000.0 * min(1.0, (n / 60000.0) ** (1 / 3))  # ~ the stock scene's density
+    xs["position"] = rng.uniform(0.0, side, (n, 3)).astype(np.float32)
+    xs["velocity"] = rng.normal(0.0, 2.0, (n, 3)).astype(np.float32)
+    xs["velocity"][: n // 200] *= 20.0
+    xs["colour"] = rng.uniform(0.0, 1.0, (n, 4)).astype(np.float32)
+    cpu = xs.copy()
+    t_cpu = oracle_mod.step(H, p, cpu, taps=True)
+    for search in (None, "cells"):
+        if search:
+            monkeypatch.setenv("PBF_SEARCH", search)
+        else:
+            monkeypatch.delenv("PBF_SEARCH", raising=False)
+        gpu_xs, t_gpu, _ = run_gpu(p, xs, flags)
+        assert_integer_parity(t_gpu, t_cpu)
+        assert np.array_equal(gpu_xs["id"], cpu["id"]) and np.array_equal(gpu_xs["colour"], cpu["colour"])
+        tol = 1e-6 if flags & FLAG_STRICT_FP else 1e-4
+        assert np.allclose(t_gpu["lambda"], t_cpu["lambda"], rtol=tol, atol=tol * np.abs(t_cpu["lambda"]).max())
+        assert np.allclose(t_gpu["rho"], t_cpu["rho"], rtol=tol, atol=tol * np.abs(t_cpu["rho"]).max())
+        # a random cloud is as ill-conditioned as the t=0 lattice (SURVEY F4): positions only loosely in the fast mode
+        pos_tol = (1e-6 if flags & FLAG_STRICT_FP else 1e-3) * DOMAIN
+        assert frac_within(gpu_xs["position"], cpu["position"], pos_tol) >= 0.995
