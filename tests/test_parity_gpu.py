@@ -251,3 +251,26 @@ def test_random_clouds(gpu, oracle_mod, monkeypatch, seed, n, flags):
         # a random cloud is as ill-conditioned as the t=0 lattice: positions only loosely in the fast mode
         pos_tol = (1e-6 if flags & FLAG_STRICT_FP else 1e-3) * DOMAIN
         assert frac_within(gpu_xs["position"], cpu["position"], pos_tol) >= 0.995
+
+
+def test_advance_from_a_worker_thread(gpu):
+    """visualise.cpp:85-109 calls advance() from a worker thread while the UI thread owns the process: every C entry
+    point sets the device itself, so a context created on one thread works from another (serial calls)."""
+    import threading
+    p, xs = scenes.two_cubes(4000, 3)
+    main = xs.copy()
+    with Solver(H, 0) as s:
+        for f in range(3):
+            s.advance(scenes.apply_motion(p, f), main)
+    worker, err = xs.copy(), []
+    with Solver(H, 0) as s:  # created here ...
+        def run():
+            try:
+                for f in range(3):
+                    s.advance(scenes.apply_motion(p, f), worker)  # ... driven there
+            except Exception as e:  # pragma: no cover
+                err.append(e)
+        t = threading.Thread(target=run)
+        t.start()
+        t.join()
+    assert not err and worker.tobytes() == main.tobytes()
