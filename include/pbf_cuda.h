@@ -197,6 +197,11 @@ int pbf_query_result(pbf_ctx *ctx, uint32_t index, uint64_t *ids, uint64_t capac
  * non-indexed, triangles ordered by marching-cube index.  Each pointer may be NULL to skip it. */
 int pbf_mesh_download(pbf_ctx *ctx, float *vs, float *ns, float *cs, uint64_t capacity_vertices);
 
+/* Device-side hand-off of the same mesh (for a renderer that maps CUDA memory, e.g. CUDA-GL interop in a `visualise`
+ * driver, visualise.cpp:29-197): device pointers to vs/ns (3 floats per vertex) and cs (4 floats per vertex), valid
+ * until the next step on this context.  The stream is synchronised before returning. */
+int pbf_mesh_device(pbf_ctx *ctx, const float **vs, const float **ns, const float **cs, uint64_t *n_vertices);
+
 /* ---- resident path (no host round trip between steps) ------------------------------------------ */
 int pbf_upload(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n);
 int pbf_step(pbf_ctx *ctx, const pbf_params *params);          /* enqueue one step (asynchronous) */

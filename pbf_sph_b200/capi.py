@@ -122,7 +122,8 @@ class Scene:
 # every symbol include/pbf_cuda.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = [
     "pbf_create", "pbf_destroy", "pbf_last_error", "pbf_abi_version", "pbf_set_flags", "pbf_set_stream",
-    "pbf_advance_host", "pbf_advance_scene_host", "pbf_query_result", "pbf_set_scene", "pbf_mesh_download", "pbf_upload",
+    "pbf_advance_host", "pbf_advance_scene_host", "pbf_query_result", "pbf_set_scene", "pbf_mesh_download",
+    "pbf_mesh_device", "pbf_upload",
     "pbf_step", "pbf_sync", "pbf_download",
     "pbf_particle_count", "pbf_device_state", "pbf_grid", "pbf_debug_read", "pbf_profile_reset", "pbf_profile_read",
     "pbf_launch_count", "pbf_dist_unique_id", "pbf_dist_init", "pbf_dist_init_local", "pbf_dist_upload",
@@ -163,6 +164,7 @@ def lib() -> C.CDLL:
         "pbf_query_result": ([vp, u32, vp, u64, P(u64)], i32),
         "pbf_set_scene": ([vp, P(SceneStruct)], i32),
         "pbf_mesh_download": ([vp, vp, vp, vp, u64], i32),
+        "pbf_mesh_device": ([vp, P(vp), P(vp), P(vp), P(u64)], i32),
         "pbf_upload": ([vp, vp, u64], i32),
         "pbf_step": ([vp, P(Params)], i32),
         "pbf_sync": ([vp], i32),

@@ -430,6 +430,17 @@ int pbf_mesh_download(pbf_ctx *ctx, float *vs, float *ns, float *cs, uint64_t ca
   return PBF_OK;
 }
 
+int pbf_mesh_device(pbf_ctx *ctx, const float **vs, const float **ns, const float **cs, uint64_t *n_vertices) {
+  PBF_ENTER(ctx);
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const uint64_t nv = ctx->n_triangles * 3;
+  if (n_vertices) *n_vertices = nv;
+  if (vs) *vs = nv ? ctx->mesh_vs.p : nullptr;
+  if (ns) *ns = nv ? ctx->mesh_ns.p : nullptr;
+  if (cs) *cs = nv ? ctx->mesh_cs.p : nullptr;
+  return PBF_OK;
+}
+
 int pbf_upload(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n) {
   PBF_ENTER(ctx);
   if (n && !xs) return fail(ctx, PBF_ERR_INVALID, "xs", "NULL");

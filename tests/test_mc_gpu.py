@@ -45,3 +45,28 @@ def test_surface_off_gives_empty_mesh(gpu):
     with Solver(H, 0) as s:
         res = s.advance(p, xs)
         assert len(res.vs) == 0 and s.grid().n_triangles == 0
+
+
+def test_device_mesh_handoff(gpu):
+    """pbf_mesh_device: the mesh where it was produced (for a renderer mapping CUDA memory) equals the host download."""
+    import ctypes as C
+    p, xs = scenes.two_cubes(4000, 3)
+    p.surface_enabled = 1
+    with Solver(H, 0) as s:
+        for f in range(6):
+            res = s.advance(scenes.apply_motion(p, f), xs)
+        vs, ns, cs, nv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        s._ck(s._L.pbf_mesh_device(s._ctx, C.byref(vs), C.byref(ns), C.byref(cs), C.byref(nv)))
+        assert nv.value == len(res.vs) > 0 and vs.value and ns.value and cs.value
+        rt = None
+        for name in ("libcudart.so.12", "libcudart.so", "/usr/local/cuda/lib64/libcudart.so"):
+            try:
+                rt = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        assert rt is not None, "CUDA runtime not found"
+        for ptr, want in ((vs, res.vs), (ns, res.ns), (cs, res.cs)):
+            host = np.empty_like(want)
+            assert rt.cudaMemcpy(C.c_void_p(host.ctypes.data), ptr, C.c_size_t(host.nbytes), 2) == 0  # DeviceToHost
+            assert np.array_equal(host, want, equal_nan=True)
