@@ -221,7 +221,9 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
         per_step_bytes = float(moved_t.item()) / e2e_steps * PARTICLE.itemsize
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak" if name == "dam-weak" else "strong",  # a fixed-size --workload split over the ranks is strong scaling
+            "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "name": name, "particles": n_total, "solver_iterations": iters,
                        "settle_steps": args.settle, "decomposition": "Z-curve slabs, NCCL send/recv halo per solver iteration",
