@@ -176,6 +176,10 @@ def workload(name: str, world: int):
         side = int(round((1_000_000 * world) ** (1 / 3)))
         p, xs = scenes.dam_break(side, 4)
         return name, f"dam-break {side}^3 = {side ** 3} particles ({world} GPUs, ~1 M per GPU), 4 solver iterations", p, xs
+    if name == "dam-weak-8m":  # BASELINE.json configs[4]: weak scaling 8 M -> 64 M particles, 8 solver iterations
+        side = int(round((8_000_000 * world) ** (1 / 3)))
+        p, xs = scenes.dam_break(side, 8)
+        return name, f"dam-break {side}^3 = {side ** 3} particles ({world} GPUs, ~8 M per GPU), 8 solver iterations", p, xs
     raise SystemExit(f"unknown workload {name}")
 
 

@@ -222,7 +222,7 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak" if name == "dam-weak" else "strong",  # a fixed-size --workload split over the ranks is strong scaling
+            "scaling": "weak" if name.startswith("dam-weak") else "strong",  # a fixed-size --workload split over the ranks is strong scaling
             "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "name": name, "particles": n_total, "solver_iterations": iters,
