@@ -72,7 +72,7 @@ def test_slab_group_dam_break_balance_and_parity(gpu):
     assert np.array_equal(a["id"], b["id"])
     assert np.array_equal(a["position"].view(np.uint32), b["position"].view(np.uint32))
     owned = [s["owned"] for s in stats[-1]]
-    assert max(owned) < 1.25 * len(xs) / 4, owned  # histogram splits balance the particle counts
+    assert max(owned) < 1.4 * len(xs) / 4, owned  # histogram splits balance the (density-weighted) particle counts
     ring1 = sum(s["ghost_ring1"] for s in stats[-1])
     ghosts = sum(s["ghosts"] for s in stats[-1])
     assert 0 < ring1 < ghosts  # lambda is computed for the inner ghost ring only
