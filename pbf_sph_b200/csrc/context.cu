@@ -304,7 +304,7 @@ int pbf_create(pbf_ctx **out, float h, int device) {
   }
   ctx->own_stream = true;
   if (const char *e = getenv("PBF_LIST_CAP")) ctx->list_cap = atoi(e) == 64 ? 64 : (int)kListMax;
-  if (const char *e = getenv("PBF_SEARCH")) ctx->search_mode = (e[0] == 'c') ? 1 : ((e[0] == 'f') ? 2 : 0);
+  if (const char *e = getenv("PBF_SEARCH")) ctx->search_mode = (e[0] == 'c') ? 1 : 0;
   *out = ctx;
   return PBF_OK;
 }

@@ -152,132 +152,6 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
   if (rho_out) rho_out[a] = rho;
 }
 
-// ---- the same pass with a FLAT candidate loop (PBF_SEARCH=flat).
-//
-// In lambda_list_kernel every lane walks 18 runs of its own and the warp pays, run by run, for the longest one: with
-// ~5 cells per warp the run loops execute at ~21 of 32 lanes.  Here the runs of a cell are looked up ONCE per cell of
-// the block (not once per particle) into a shared-memory table, and every lane consumes its cell's runs as one
-// stream of candidates — the warp pays for the lane with the most candidates in total (+9 %), not for the sum of the
-// per-run maxima (+37 %).  Candidate positions are fetched four ahead.  Lists, counts and sums are those of
-// lambda_list_kernel, bit for bit.
-constexpr int kFlatCells = 40;  // cells of one block staged at a time (a 128-particle block spans ~21 in the bulk)
-constexpr uint32_t kNone = 0xFFFFFFFFu;
-
-template <bool kStrict, int kCap>
-__global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_flat_kernel(StepConst c, uint32_t first, uint32_t count,
-                                                             const uint32_t *__restrict__ keys,
-                                                             const uint32_t *__restrict__ table,
-                                                             const float4 *__restrict__ pos_mass,
-                                                             const float4 *__restrict__ pstar_in,
-                                                             float4 *__restrict__ pstar_out, float *__restrict__ rho_out,
-                                                             uint32_t *nl, uint32_t stride, uint32_t inv_stride,
-                                                             uint32_t *__restrict__ n_hits,
-                                                             const uint32_t *__restrict__ role, uint32_t want) {
-  __shared__ uint2 s_runs[kFlatCells][18];
-  __shared__ uint32_t s_key[kFlatCells];
-  __shared__ uint32_t s_warp[kBlock / 32];
-  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
-  const bool valid = t < count;
-  const uint32_t a = first + (valid ? t : 0u);
-  const uint32_t key = valid ? __ldg(keys + a) : kNone;
-  // cells of this block: a particle whose predecessor in the block has another key starts one
-  const bool head = valid && (threadIdx.x == 0 || __ldg(keys + a - 1) != key);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
-  if (lane == 0) s_warp[warp] = __popc(heads);
-  __syncthreads();
-  uint32_t ord = __popc(heads & ((2u << lane) - 1u)) - 1u, ncell = 0;  // ordinal of this particle's cell in the block
-#pragma unroll
-  for (unsigned w = 0; w < kBlock / 32; ++w) {
-    const uint32_t h = s_warp[w];
-    ord += w < warp ? h : 0u;
-    ncell += h;
-  }
-  const bool active = valid && (!role || (__ldg(role + a) & want));
-  float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) pa = ldg4(pstar_in + a);
-
-  // ---- phase 1: find the hits
-  uint32_t *w_ptr = nl + a;  // next free entry of this particle's column: hit k lives at nl[k * stride + a]
-  bool bail = false;         // the list might overflow: leave it, both passes take the one-pass walk for this particle
-  for (uint32_t c0 = 0; c0 < ncell; c0 += kFlatCells) {
-    if (c0) __syncthreads();  // the previous batch's tables are no longer read
-    const uint32_t local = ord - c0;  // (unsigned: cells of earlier batches compare as huge)
-    if (head && local < (uint32_t)kFlatCells) s_key[local] = key;
-    __syncthreads();
-    const uint32_t nb = min(ncell - c0, (uint32_t)kFlatCells);
-    for (uint32_t p = threadIdx.x; p < nb * 9u; p += kBlock) {
-      const uint32_t cell = p / 9u, row = p - 9u * cell, ck = s_key[cell];
-      const uint32_t kx = ck & kAxisMask, ky = (ck >> 1) & kAxisMask, kz = (ck >> 2) & kAxisMask;
-      const uint32_t xm = dilated_dec(kx), xp = dilated_inc(kx);
-      const bool x_even = (kx & 1u) == 0u;
-      const uint32_t iz = row / 3u, iy = row - 3u * iz;
-      const uint32_t my = (iy == 0 ? dilated_dec(ky) : (iy == 1 ? ky : dilated_inc(ky))) << 1;
-      const uint32_t mz = (iz == 0 ? dilated_dec(kz) : (iz == 1 ? kz : dilated_inc(kz))) << 2;
-      const RowRuns rr = load_row(table, c.G, mz | my, x_even ? kx : xm, x_even ? xm : xp);
-      // order along x is (x-1, x, x+1): the single cell comes first when x is even, last when x is odd
-      s_runs[cell][2u * row] = x_even ? make_uint2(rr.ss, rr.se) : make_uint2(rr.ps, rr.pe);
-      s_runs[cell][2u * row + 1u] = x_even ? make_uint2(rr.ps, rr.pe) : make_uint2(rr.ss, rr.se);
-    }
-    __syncthreads();
-    if (!active || local >= (uint32_t)kFlatCells) continue;
-    const uint2 *my_runs = s_runs[local];
-    uint32_t r = 0, b = 0, e = 0;
-    auto next = [&]() -> uint32_t {  // the next candidate of this particle, kNone when there is none left
-      if (b == e) {
-        for (;;) {
-          if (r == 18u) return kNone;
-          const uint2 q = my_runs[r++];
-          if (q.x != q.y) { b = q.x; e = q.y; break; }
-        }
-        // hits so far (exact: the column pointer advanced by stride per hit) + up to 4 candidates still in flight
-        const uint32_t k = __umulhi((uint32_t)(w_ptr - (nl + a)), inv_stride);
-        if (k + 4u + (e - b) > (uint32_t)kCap) { bail = true; r = 18u; e = b; return kNone; }
-      }
-      return b++;
-    };
-    auto fetch = [&](uint32_t i) { return ldg4(pstar_in + (i == kNone ? a : i)); };
-    uint32_t i0 = next(), i1 = next(), i2 = next(), i3 = next();
-    float4 q0 = fetch(i0), q1 = fetch(i1), q2 = fetch(i2), q3 = fetch(i3);
-    auto stage = [&](uint32_t &i, float4 &q) {
-      const bool hit = LambdaAcc<kStrict>::test(c, pa, q);
-      store_if(w_ptr, i, hit);
-      w_ptr += hit ? stride : 0u;
-      i = next();
-      q = fetch(i);
-    };
-    while (i0 != kNone) {
-      stage(i0, q0);
-      if (i1 == kNone) break;
-      stage(i1, q1);
-      if (i2 == kNone) break;
-      stage(i2, q2);
-      if (i3 == kNone) break;
-      stage(i3, q3);
-    }
-  }
-  if (!active) return;
-  const uint32_t k = bail ? (uint32_t)kCap + 1u : __umulhi((uint32_t)(w_ptr - (nl + a)), inv_stride);
-  n_hits[a] = k;
-
-  // ---- phase 2: the sums over the hits
-  const float mass = __ldg(&pos_mass[a].w);
-  LambdaAcc<kStrict> acc;
-  acc.init();
-  acc.set_mass(mass);
-  if (k <= (uint32_t)kCap) {
-    const uint32_t *row = nl + a;
-#pragma unroll 4
-    for (uint32_t i = 0; i < k; ++i, row += stride) acc.add_in(c, pa, ldg4(pstar_in + __ldcs(row)));
-  } else {
-    for_each_candidate(key, c.G, table, [&](uint32_t b2) { acc.add(c, pa, ldg4(pstar_in + b2)); });
-  }
-  float rho;
-  const float lambda = acc.finish(c, mass, rho);
-  pstar_out[a] = make_float4(pa.x, pa.y, pa.z, lambda);
-  if (rho_out) rho_out[a] = rho;
-}
-
 template <bool kStrict, int kCap>
 __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) delta_list_kernel(StepConst c, uint32_t first, uint32_t count,
                                                             const uint32_t *__restrict__ keys,
@@ -357,18 +231,6 @@ template <int kCap> int launch_lambda_cap(pbf_ctx *ctx, uint32_t first, uint32_t
       lambda_sums_kernel<false, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
           ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, ctx->nl_count.p,
           role, want);
-    PBF_LAUNCH_CHECK(ctx);
-    return PBF_OK;
-  }
-  if (ctx->search_mode == 2) {  // flat candidate loop over per-cell run tables (PBF_SEARCH=flat)
-    if (ctx->flags & PBF_FLAG_STRICT_FP)
-      lambda_flat_kernel<true, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-          ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride,
-          (uint32_t)(((1ull << 32) + stride - 1) / stride), ctx->nl_count.p, role, want);
-    else
-      lambda_flat_kernel<false, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-          ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride,
-          (uint32_t)(((1ull << 32) + stride - 1) / stride), ctx->nl_count.p, role, want);
     PBF_LAUNCH_CHECK(ctx);
     return PBF_OK;
   }
