@@ -47,6 +47,17 @@ __device__ __forceinline__ void store_if(uint32_t *p, uint32_t v, bool pred) {
       : "memory");
 }
 
+// The append of the search loop: store the candidate's index at the particle's next free slot and advance the slot,
+// both under the hit predicate (@p STG + @p IADD: two instructions, where `slot += hit ? stride : 0` costs a select
+// and an add on top of the store).
+__device__ __forceinline__ void append_if(uint32_t *nl, uint32_t &slot, uint32_t v, uint32_t stride, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.cs.b32 [%1], %2;\n\t@q add.u32 %0, %0, %4;\n\t}"
+      : "+r"(slot)
+      : "l"(nl + slot), "r"(v), "r"((uint32_t)pred), "r"(stride)
+      : "memory");
+}
+
 // cell-table bounds of one (y,z) row of the 27-cell neighbourhood: the merged pair run and the single cell
 struct RowRuns {
   uint32_t ps, pe, ss, se;
@@ -107,9 +118,7 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
     if (k + (e - s) <= (uint32_t)kCap) {  // cannot overflow: no per-candidate capacity test, no hit counter
 #pragma unroll 4
       for (uint32_t b = s; b < e; ++b) {
-        const bool hit = LambdaAcc<kStrict>::test(c, pa, ldg4(pstar_in + b));
-        store_if(nl + slot, b, hit);
-        slot += hit ? stride : 0u;
+        append_if(nl, slot, b, stride, LambdaAcc<kStrict>::test(c, pa, ldg4(pstar_in + b)));
       }
     } else {
 #pragma unroll 1
