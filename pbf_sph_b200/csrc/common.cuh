@@ -218,7 +218,8 @@ struct pbf_ctx {
   // per-iteration neighbour list: nl[k * nl_stride + particle] = k-th in-radius candidate, nl_count[particle] = hits
   pbf::DevBuf<uint32_t> nl, nl_count;
   uint32_t nl_stride = 0;
-  int list_cap = 96;  // hits kept per particle in the neighbour list (kListMax, or 64 via PBF_LIST_CAP for A/B runs)
+  int list_cap = 192;     // hits kept per particle in the neighbour list: kListWide, or 96 / 64 via PBF_LIST_CAP (A/B runs)
+  uint32_t nl_cap = 96;   // the capacity the current list was written with (neighbour_list.cu)
   // per-step plan of the warp-per-cell search (cell_search.cu): cells to search, their targets and flat candidate lists
   pbf::DevBuf<uint32_t> plan_heads, plan_cand;
   pbf::DevBuf<uint4> plan_info;
@@ -304,7 +305,8 @@ int launch_lambda_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uin
 int launch_delta_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
                         const uint32_t *table, const float4 *pstar_in, float4 *pstar_out);
 // neighbour-list kernels (neighbour_list.cu): the production lambda/delta passes
-constexpr uint32_t kListMax = 96;  // hits stored per particle; beyond that the particle takes the one-pass path
+constexpr uint32_t kListMax = 96;    // hits stored per particle by the warp-per-cell search (its staged lists)
+constexpr uint32_t kListWide = 192;  // ... and by the production search; beyond that the particle takes the one-pass path
 int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                        const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
                        const uint32_t *role = nullptr, uint32_t want = 0);

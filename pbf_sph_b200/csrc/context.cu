@@ -303,7 +303,7 @@ int pbf_create(pbf_ctx **out, float h, int device) {
     return PBF_ERR_CUDA;
   }
   ctx->own_stream = true;
-  if (const char *e = getenv("PBF_LIST_CAP")) ctx->list_cap = atoi(e) == 64 ? 64 : (int)kListMax;
+  if (const char *e = getenv("PBF_LIST_CAP")) ctx->list_cap = atoi(e) == 64 ? 64 : (atoi(e) == 96 ? (int)kListMax : (int)kListWide);
   if (const char *e = getenv("PBF_SEARCH")) ctx->search_mode = (e[0] == 'c') ? 1 : 0;
   *out = ctx;
   return PBF_OK;

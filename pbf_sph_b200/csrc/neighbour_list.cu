@@ -277,21 +277,33 @@ int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint3
   if (count == 0) return PBF_OK;
   const uint32_t n = ctx->sc.n;
   const uint32_t stride = (n + 31u) & ~31u;  // rows start on 128-byte boundaries
-  if ((uint64_t)stride * (kListMax + 1) >= (1ull << 32))
+  // Rows cost address space, not bandwidth (a row is touched only by particles with that many hits), so the thread-per-
+  // particle search keeps up to kListWide hits: while a dam break splashes, particles clamped onto the walls pile up
+  // (dam-1m after 30 steps: 431 particles with 97..229 neighbours) and every one that overflows drags its block through
+  // the one-pass fallback in both passes.  The wide list needs n < 2^32 / 193 = 22 M particles per device; above that,
+  // and for the warp-per-cell search (its staged lists are kListMax long), the list is kListMax deep.
+  uint32_t cap = (uint32_t)ctx->list_cap;
+  if (cap == kListWide && (ctx->search_mode == 1 || (uint64_t)stride * (kListWide + 1) >= (1ull << 32))) cap = kListMax;
+  if ((uint64_t)stride * (cap + 1) >= (1ull << 32))
     return fail(ctx, PBF_ERR_INVALID, "n", "too many particles on one device (neighbour-list indexing)");
-  PBF_CUDA(ctx, ctx->nl.reserve((size_t)stride * (kListMax + 1)));  // + the dump row of cell_search.cu
+  PBF_CUDA(ctx, ctx->nl.reserve((size_t)stride * (cap + 1)));  // + the dump row of cell_search.cu
   PBF_CUDA(ctx, ctx->nl_count.reserve(n));
   ctx->nl_stride = stride;
-  if (ctx->list_cap == 64)
+  ctx->nl_cap = cap;
+  if (cap == 64)
     return launch_lambda_cap<64>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
+  if (cap == kListWide)
+    return launch_lambda_cap<kListWide>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
   return launch_lambda_cap<kListMax>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
 }
 
 int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                       const float4 *pstar_in, float4 *pstar_out, const uint32_t *role, uint32_t want) {
   if (count == 0) return PBF_OK;
-  if (ctx->list_cap == 64)
+  if (ctx->nl_cap == 64)  // the capacity the lambda pass of this iteration wrote the list with
     return launch_delta_cap<64>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
+  if (ctx->nl_cap == kListWide)
+    return launch_delta_cap<kListWide>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
   return launch_delta_cap<kListMax>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
 }
 

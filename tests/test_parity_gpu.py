@@ -184,6 +184,36 @@ def test_warp_per_cell_search_is_bit_identical(gpu, oracle_mod, warm_s0, monkeyp
         assert alt.tobytes() == ref.tobytes()
 
 
+@pytest.mark.parametrize("flags", [0, FLAG_STRICT_FP])
+def test_piled_particles_wide_list_against_oracle_and_narrow_list(gpu, oracle_mod, monkeypatch, flags):
+    """While a dam break splashes, particles clamped onto the walls pile up: 97..229 in-radius neighbours at 1 M
+    particles.  Clumps of 110 particles (more hits than the 96-deep list of the A/B modes, fewer than the production
+    192) take the list path by default and the one-pass fallback under PBF_LIST_CAP=96: same neighbour sets, same
+    summation order, so lambda and the step agree with the oracle either way, and bit for bit with each other in the
+    strict arithmetic."""
+    rng = np.random.default_rng(11)
+    p, xs = scenes.two_cubes(6000, 3)
+    for k in range(6):  # six clumps of 110 particles, each inside a cube of 0.4 h (= 20 unscaled units)
+        sel = slice(110 * k, 110 * (k + 1))
+        centre = xs["position"][110 * k].copy()
+        xs["position"][sel] = centre + rng.uniform(-10.0, 10.0, (110, 3)).astype(np.float32)
+    cpu = xs.copy()
+    t_cpu = oracle_mod.step(H, p, cpu, taps=True)
+    assert 96 < t_cpu["nbr_count"].max() <= 192
+    runs = {}
+    for cap in ("192", "96"):
+        monkeypatch.setenv("PBF_LIST_CAP", cap)
+        runs[cap] = run_gpu(p, xs, flags)
+        gpu_xs, t_gpu, _ = runs[cap]
+        assert_integer_parity(t_gpu, t_cpu)
+        tol = 1e-6 if flags & FLAG_STRICT_FP else 1e-4
+        assert np.allclose(t_gpu["lambda"], t_cpu["lambda"], rtol=tol, atol=tol * np.abs(t_cpu["lambda"]).max()), cap
+        assert np.allclose(t_gpu["rho"], t_cpu["rho"], rtol=tol, atol=tol * np.abs(t_cpu["rho"]).max()), cap
+    if flags & FLAG_STRICT_FP:
+        assert np.array_equal(runs["192"][1]["lambda"], runs["96"][1]["lambda"])
+        assert runs["192"][0].tobytes() == runs["96"][0].tobytes()
+
+
 def test_obstacle_rejected(gpu):
     p, xs = scenes.two_cubes(2000, 2)
     xs["type"][5] = 1

@@ -1,5 +1,1 @@
-CMD="python bench.py --steps 3 --warmup 3 --settle 30 --no-cpu-baseline --no-e2e"
-for m in sm grid; do
-PBF_TILES=$m ncu --set full --clock-control none -k regex:"lambda_list|delta_list" -s 200 -c 2 -o gpurun_out/tiles_$m -f $CMD > gpurun_out/tiles_$m.log 2>&1
-done
-ls -la gpurun_out/tiles_*
+python -m pytest tests/test_parity_gpu.py tests/test_dist_gpu.py tests/test_extensions_gpu.py tests/test_scene_gpu.py -x -q -m gpu 2>&1 | tail -3
