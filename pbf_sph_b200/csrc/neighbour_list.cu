@@ -116,9 +116,22 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
     // hits so far, exactly: (slot - a) is a small multiple of stride, inv_stride = ceil(2^32 / stride)
     uint32_t k = __umulhi(slot - a, inv_stride);
     if (k + (e - s) <= (uint32_t)kCap) {  // cannot overflow: no per-candidate capacity test, no hit counter
-#pragma unroll 4
-      for (uint32_t b = s; b < e; ++b) {
-        append_if(nl, slot, b, stride, LambdaAcc<kStrict>::test(c, pa, ldg4(pstar_in + b)));
+      // Whole batches of four, then ONE masked batch for the 1-3 left over: its gathers go out together (indices
+      // clamped into the run), where a scalar remainder loop waits out one gather latency per candidate.
+      uint32_t b = s;
+      for (; b + 4u <= e; b += 4u) {
+        const float4 q0 = ldg4(pstar_in + b), q1 = ldg4(pstar_in + b + 1), q2 = ldg4(pstar_in + b + 2), q3 = ldg4(pstar_in + b + 3);
+        append_if(nl, slot, b, stride, LambdaAcc<kStrict>::test(c, pa, q0));
+        append_if(nl, slot, b + 1u, stride, LambdaAcc<kStrict>::test(c, pa, q1));
+        append_if(nl, slot, b + 2u, stride, LambdaAcc<kStrict>::test(c, pa, q2));
+        append_if(nl, slot, b + 3u, stride, LambdaAcc<kStrict>::test(c, pa, q3));
+      }
+      if (b < e) {
+        const uint32_t last = e - 1u;
+        const float4 q0 = ldg4(pstar_in + b), q1 = ldg4(pstar_in + min(b + 1u, last)), q2 = ldg4(pstar_in + min(b + 2u, last));
+        append_if(nl, slot, b, stride, LambdaAcc<kStrict>::test(c, pa, q0));
+        append_if(nl, slot, b + 1u, stride, b + 1u < e && LambdaAcc<kStrict>::test(c, pa, q1));
+        append_if(nl, slot, b + 2u, stride, b + 2u < e && LambdaAcc<kStrict>::test(c, pa, q2));
       }
     } else {
 #pragma unroll 1
