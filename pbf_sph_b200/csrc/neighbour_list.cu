@@ -58,6 +58,38 @@ __device__ __forceinline__ void append_if(uint32_t *nl, uint32_t &slot, uint32_t
       : "memory");
 }
 
+// The sums over one particle's hit list, in list (= the reference's visiting) order: batches of kW (kW list entries,
+// then kW position gathers in flight), then ONE masked batch for the 1..kW-1 hits left over — a scalar remainder loop
+// waits out two dependent latencies (list entry, then position) per hit.  kW = 8 in the delta pass; 4 in the lambda
+// pass, whose search loop needs the registers (56 -> 9 blocks per SM).
+template <int kW, typename Acc>
+__device__ __forceinline__ void sum_over_hits(Acc &acc, const StepConst &c, const float4 pa, const float4 *__restrict__ pstar,
+                                              const uint32_t *row, uint32_t stride, uint32_t k, uint32_t self) {
+  uint32_t i = 0;
+  for (; i + kW <= k; i += kW, row += kW * stride) {
+    uint32_t b[kW];
+    float4 q[kW];
+#pragma unroll
+    for (int m = 0; m < kW; ++m) b[m] = __ldcs(row + m * stride);
+#pragma unroll
+    for (int m = 0; m < kW; ++m) q[m] = ldg4(pstar + b[m]);
+#pragma unroll
+    for (int m = 0; m < kW; ++m) acc.add_in(c, pa, q[m]);
+  }
+  const uint32_t left = k - i;
+  if (left) {
+    uint32_t b[kW - 1];
+    float4 q[kW - 1];
+#pragma unroll
+    for (int m = 0; m < kW - 1; ++m) b[m] = (uint32_t)m < left ? __ldcs(row + m * stride) : self;
+#pragma unroll
+    for (int m = 0; m < kW - 1; ++m) q[m] = ldg4(pstar + b[m]);
+#pragma unroll
+    for (int m = 0; m < kW - 1; ++m)
+      if ((uint32_t)m < left) acc.add_in(c, pa, q[m]);
+  }
+}
+
 // cell-table bounds of one (y,z) row of the 27-cell neighbourhood: the merged pair run and the single cell
 struct RowRuns {
   uint32_t ps, pe, ss, se;
@@ -162,9 +194,7 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
   acc.init();
   acc.set_mass(mass);
   if (k <= (uint32_t)kCap) {
-    const uint32_t *row = nl + a;
-#pragma unroll 4
-    for (uint32_t i = 0; i < k; ++i, row += stride) acc.add_in(c, pa, ldg4(pstar_in + __ldcs(row)));
+    sum_over_hits<4>(acc, c, pa, pstar_in, nl + a, stride, k, a);
   } else {
     for_each_candidate(key, c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
@@ -192,11 +222,7 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) delta_list_kernel(StepCon
   DeltaAcc<kStrict> acc;
   acc.init();
   if (k <= (uint32_t)kCap) {
-    const uint32_t *row = nl + a;
-#pragma unroll 8
-    for (uint32_t i = 0; i < k; ++i, row += stride) {
-      acc.add_in(c, pa, ldg4(pstar_in + __ldcs(row)));  // add_in skips the particle itself (r < EPSILON)
-    }
+    sum_over_hits<8>(acc, c, pa, pstar_in, nl + a, stride, k, a);  // add_in skips the particle itself (r < EPSILON)
   } else {
     for_each_candidate(__ldg(keys + a), c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
@@ -226,9 +252,7 @@ __global__ void __launch_bounds__(kBlock) lambda_sums_kernel(StepConst c, uint32
   acc.init();
   acc.set_mass(mass);
   if (k <= (uint32_t)kCap) {
-    const uint32_t *row = nl + a;
-#pragma unroll 4
-    for (uint32_t i = 0; i < k; ++i, row += stride) acc.add_in(c, pa, ldg4(pstar_in + __ldcs(row)));
+    sum_over_hits<8>(acc, c, pa, pstar_in, nl + a, stride, k, a);
   } else {
     for_each_candidate(__ldg(keys + a), c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
