@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
 }
 
 template <bool kStrict, int kCap>
-__global__ void __launch_bounds__(kBlock, PBF_NL_MINB) delta_list_kernel(StepConst c, uint32_t first, uint32_t count,
+__global__ void __launch_bounds__(kBlock, 8) delta_list_kernel(StepConst c, uint32_t first, uint32_t count,
                                                             const uint32_t *__restrict__ keys,
                                                             const uint32_t *__restrict__ table,
                                                             const float4 *__restrict__ pstar_in,
