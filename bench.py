@@ -271,8 +271,9 @@ def roofline_of(prof, n, iters, steps):
     return {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "bytes_per_particle": ALG_BYTES[fam], "avg_launch_ms": avg_ms,
-            "note": "the neighbour passes are bound by the L1 data pipe and instruction issue (~170 candidate pairs per "
-                    "particle, one 16-byte position through L1 per pair and lane), not by HBM; see DESIGN.md §4 and "
+            "note": "the neighbour passes are bound by the latency of their gathers, the L1 data pipe and instruction issue "
+                    "(~195 candidate pairs per particle, one 16-byte position through L1 per pair and lane), not by HBM; "
+                    "`issue` is the fraction of the warp-instruction issue slots; see DESIGN.md §4 and "
                     "profiles/r01c_search_experiments.txt", "ms_per_step_by_family": breakdown,
             "achieved_GBps_by_family": per_kernel}
 
@@ -327,6 +328,21 @@ def run_single(args):
     roofline = roofline_of(prof, n, iters, args.steps)
     roofline["region"] = (f"{args.steps} further steps with per-family CUDA events recorded by the library on its stream "
                           f"({ms_profiled / args.steps:.4f} ms/step with events, {ms_total / args.steps:.4f} without)")
+    # the ceiling that does apply to the neighbour passes: warp-instruction issue slots (SMs x 4 schedulers x SM clock);
+    # instructions per launch from the committed ncu capture, duration live
+    tf = ROOT / "profiles" / "ncu_traffic.json"
+    if tf.exists():
+        t = json.loads(tf.read_text())
+        inst = t.get("warp_inst_per_launch", {}).get(roofline["kernel"])
+        clocks = clk.summary()
+        if inst and t.get("particles") == n and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6 / 1e9
+            got = inst / (roofline["avg_launch_ms"] * 1e-3) / 1e9
+            roofline["issue"] = {"achieved": got, "peak": peak_issue, "unit": "G warp-inst/s", "frac": got / peak_issue,
+                                 "warp_inst_per_launch": inst,
+                                 "source": "smsp__inst_executed.sum of one launch (" + t.get("source", "ncu") + "); peak = "
+                                           f"{sms} SMs x 4 schedulers x {clocks['sm_mhz']:.0f} MHz"}
 
     # end to end through the drop-in call, pinned host buffers
     snap = s.download()
