@@ -42,9 +42,15 @@ template <typename T, typename N, template <size_t, typename> typename V> class 
   }
 
 public:
-  explicit Solver(N h, int device = 0) : h(h) {
+  // pinCallerMemory: page-lock the caller's std::vector storage while it keeps coming back (PBF_FLAG_PIN_HOST), so that
+  // the copies of advance() run at the PCIe rate instead of through the runtime's pageable staging.  Safe whenever the
+  // caller keeps its vector alive between calls, as both reference drivers do (benchmark.cpp:22-58, visualise.cpp:85-109);
+  // this adaptor releases the lock itself before it grows the vector.  Call unpin() before freeing the vector early.
+  explicit Solver(N h, int device = 0, bool pinCallerMemory = false) : h(h) {
     if (pbf_create(&ctx, h, device) != PBF_OK) raise("pbf_create");
+    if (pinCallerMemory && pbf_set_flags(ctx, PBF_FLAG_PIN_HOST) != PBF_OK) raise("pbf_set_flags");
   }
+  void unpin() { pbf_unpin_host(ctx); }
   ~Solver() override { pbf_destroy(ctx); }
   Solver(const Solver &) = delete;
   Solver &operator=(const Solver &) = delete;
@@ -87,6 +93,7 @@ public:
       emitted += size_t(std::floor(side)) * size_t(std::ceil(side));
     }
     const size_t n = xs.size();
+    if (n + emitted > xs.capacity()) pbf_unpin_host(ctx);  // the resize below moves the storage
     xs.resize(n + emitted);
     const pbf_params p = toParams(config);
     uint64_t nv = 0, n_out = 0;

@@ -123,7 +123,15 @@ enum {
    * VORTICITY_EPSILON; finalise is ompsph.hpp:256-264).  Applied to the velocities after finalise, defined in
    * csrc/xsph.cu and pinned by oracle/pbf_oracle.c; not available on the slab path. */
   PBF_FLAG_XSPH = 1u << 4,      /* v_i += C * sum_j (v_j - v_i) poly6(r_ij) */
-  PBF_FLAG_VORTICITY = 1u << 5  /* v_i += dt * VORTICITY_EPSILON * (N x omega_i) */
+  PBF_FLAG_VORTICITY = 1u << 5, /* v_i += dt * VORTICITY_EPSILON * (N x omega_i) */
+  /* Drop-in path only.  The reference's callers hand advance() a std::vector, i.e. PAGEABLE memory, which the CUDA
+   * runtime copies through its own staging buffers at a fraction of the PCIe rate.  With this flag pbf_advance_host /
+   * pbf_advance_scene_host page-lock the caller's array the first time they see it (cudaHostRegister over
+   * [xs, xs + capacity)) and keep it locked while the same array comes back, so the 56 MB each way of a 1 M-particle
+   * step move by DMA.  CONTRACT: while the context holds an array the caller must not free or reallocate it — call
+   * pbf_unpin_host first (the C++ adaptor does so before it resizes the vector, and pbf_destroy does it last).
+   * Memory that cannot be registered (already pinned, or the driver refuses) is simply copied as before. */
+  PBF_FLAG_PIN_HOST = 1u << 6
 };
 
 /* Debug taps, all in SORTED particle order unless stated (pbf_debug_read). */
@@ -177,6 +185,9 @@ int pbf_abi_version(void);
 int pbf_set_flags(pbf_ctx *ctx, uint32_t flags);
 /* Use a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own. */
 int pbf_set_stream(pbf_ctx *ctx, void *cuda_stream);
+
+/* Release the page-lock PBF_FLAG_PIN_HOST holds on the caller's particle array (no-op when none is held). */
+int pbf_unpin_host(pbf_ctx *ctx);
 
 /* ---- drop-in path: sph::Solver::advance (sph.hpp:122-124) ------------------------------------ */
 /* H2D of xs, one PBF step, D2H.  On return xs[0..n) holds the advanced particles in Z-SORTED order

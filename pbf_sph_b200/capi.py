@@ -28,6 +28,7 @@ FLAG_PROFILE = 1 << 2
 FLAG_GLOBAL_NEIGHBOURS = 1 << 3
 FLAG_XSPH = 1 << 4       # extensions, default off (no reference backend has them)
 FLAG_VORTICITY = 1 << 5
+FLAG_PIN_HOST = 1 << 6  # page-lock the caller's array in the drop-in call (see include/pbf_cuda.h for the contract)
 
 TAP_KEYS_INPUT, TAP_PERM, TAP_KEYS_SORTED, TAP_CELL_TABLE, TAP_CAND_COUNT, TAP_NBR_COUNT = range(6)
 TAP_LAMBDA, TAP_RHO, TAP_IDS, TAP_MC_FIELD, TAP_MC_COLOUR = range(6, 11)
@@ -122,7 +123,7 @@ class Scene:
 # every symbol include/pbf_cuda.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = [
     "pbf_create", "pbf_destroy", "pbf_last_error", "pbf_abi_version", "pbf_set_flags", "pbf_set_stream",
-    "pbf_advance_host", "pbf_advance_scene_host", "pbf_query_result", "pbf_set_scene", "pbf_mesh_download",
+    "pbf_advance_host", "pbf_advance_scene_host", "pbf_unpin_host", "pbf_query_result", "pbf_set_scene", "pbf_mesh_download",
     "pbf_mesh_device", "pbf_upload",
     "pbf_step", "pbf_sync", "pbf_download",
     "pbf_particle_count", "pbf_device_state", "pbf_grid", "pbf_debug_read", "pbf_profile_reset", "pbf_profile_read",
@@ -168,6 +169,7 @@ def lib() -> C.CDLL:
         "pbf_upload": ([vp, vp, u64], i32),
         "pbf_step": ([vp, P(Params)], i32),
         "pbf_sync": ([vp], i32),
+        "pbf_unpin_host": ([vp], i32),
         "pbf_download": ([vp, vp, u64, P(u64)], i32),
         "pbf_particle_count": ([vp, P(u64)], i32),
         "pbf_device_state": ([vp, P(vp), P(vp), P(vp), P(vp)], i32),

@@ -205,6 +205,8 @@ struct pbf_ctx {
   pbf::DevBuf<pbf_particle> aos;  // staging for the drop-in path
   pbf_particle *host_pinned = nullptr;
   size_t host_pinned_cap = 0;
+  void *pin_base = nullptr;  // caller array page-locked under PBF_FLAG_PIN_HOST, and its size
+  size_t pin_bytes = 0;
   // marching cubes
   pbf::DevBuf<float4> mc_pn, mc_c;
   pbf::DevBuf<uint32_t> mc_count, mc_offset;

@@ -251,6 +251,27 @@ static int upload_device(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n) {
   return PBF_OK;
 }
 
+// PBF_FLAG_PIN_HOST: page-lock the caller's array so that the H2D / D2H of the drop-in call are DMA transfers.
+static void host_unpin(pbf_ctx *ctx) {
+  if (!ctx->pin_base) return;
+  cudaHostUnregister(ctx->pin_base);
+  cudaGetLastError();  // a caller that freed the array first has broken the contract; nothing to unwind here
+  ctx->pin_base = nullptr;
+  ctx->pin_bytes = 0;
+}
+
+static void host_pin(pbf_ctx *ctx, void *p, size_t bytes) {
+  if (ctx->pin_base == p && bytes <= ctx->pin_bytes) return;  // the array we already hold
+  host_unpin(ctx);
+  if (!p || bytes < (1u << 20)) return;  // small arrays: registration costs more than it saves
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+    ctx->pin_base = p;
+    ctx->pin_bytes = bytes;
+  } else {
+    cudaGetLastError();  // already page-locked by the caller, or not registrable: plain copies work regardless
+  }
+}
+
 static int download_device(pbf_ctx *ctx, pbf_particle *xs, uint64_t n) {
   if (n == 0) return PBF_OK;
   PBF_CUDA(ctx, ctx->aos.reserve(n + 1));
@@ -309,10 +330,18 @@ int pbf_create(pbf_ctx **out, float h, int device) {
   return PBF_OK;
 }
 
+int pbf_unpin_host(pbf_ctx *ctx) {
+  PBF_ENTER(ctx);
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  host_unpin(ctx);
+  return PBF_OK;
+}
+
 void pbf_destroy(pbf_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  host_unpin(ctx);
   dist_release(ctx);
   scene_release(ctx);
   for (int i = 0; i < 2; ++i) {
@@ -375,6 +404,7 @@ int pbf_advance_scene_host(pbf_ctx *ctx, const pbf_params *params, const pbf_sce
     if (n + fresh.size() > capacity) return fail(ctx, PBF_ERR_CAPACITY, "xs", "capacity too small for the particles the sources emit");
     if (!xs && !fresh.empty()) return fail(ctx, PBF_ERR_INVALID, "xs", "NULL");
   }
+  if (ctx->flags & PBF_FLAG_PIN_HOST) host_pin(ctx, xs, (size_t)capacity * sizeof(pbf_particle));
   PBF_TRY(upload_device(ctx, xs, n));
   PBF_TRY(step_device(ctx, *params));
   // the type check result is known only now; the particle array is left untouched on failure

@@ -47,6 +47,10 @@ class Solver:
     def _ck(self, rc: int) -> None:
         check(rc, self._ctx)
 
+    def unpin_host(self) -> None:
+        """Release the page-lock FLAG_PIN_HOST holds on the caller's array (before freeing or reallocating it)."""
+        self._ck(self._L.pbf_unpin_host(self._ctx))
+
     def set_flags(self, flags: int) -> None:
         self._ck(self._L.pbf_set_flags(self._ctx, flags))
 

@@ -6,6 +6,7 @@
 //   benchmark [-i cuda] [-d N] [-n iter] [-w warmup] [-o dir] [-l] [-v] [--fp64]          reference flags
 //             [--scene 2cubes|dam] [--particles N] [--solver-iters I] [--surface on|off]     extensions
 //             [--resident]            keep the particles on the device between frames (pbf_upload/step/download)
+//             [--no-pin]              do not page-lock the particle vector (advance() then copies through pageable memory)
 //
 // Output directory (the reference's help text promises `cloud.ply, mesh.obj` but its save() only creates the
 // directory, sph.hpp:188-196): cloud.ply = binary little-endian PLY of the final particles (x y z, r g b a, id),
@@ -36,7 +37,7 @@ using Result = sph::Result<size_t, float, pbf::vec>;
 struct Options {
   std::string impl = "cuda", output = "./out_{impl}_{type}_{iter}", scene = "2cubes", device = "0", saveState, loadState;
   size_t iterations = 200, warmup = 200, particles = 20000, solverIter = 6;
-  bool list = false, verbose = false, fp64 = false, surface = true, resident = false, fountain = false, help = false;
+  bool list = false, verbose = false, fp64 = false, surface = true, resident = false, fountain = false, help = false, pin = true;
 };
 
 static void usage() {
@@ -59,7 +60,8 @@ static void usage() {
                "                              two queries (the scene of tests/helpers.py demo_scene)\n"
                "      --solver-iters=[I]      Solver iterations per step. Default: 6\n"
                "      --surface=[on|off]      Marching-cubes surface extraction each frame. Default: on\n"
-               "      --resident              Keep particles on the device between frames\n";
+               "      --resident              Keep particles on the device between frames\n"
+               "      --no-pin                Do not page-lock the particle vector for advance()'s copies\n";
 }
 
 // "-n 5", "-n5", "--iter 5", "--iter=5"
@@ -86,6 +88,7 @@ static Options parse(int argc, char **argv) {
     else if (a == "-v" || a == "--verbose") o.verbose = true;
     else if (a == "--fp64") o.fp64 = true;
     else if (a == "--resident") o.resident = true;
+    else if (a == "--no-pin") o.pin = false;
     else if (a == "--fountain") o.fountain = true;
     else if (take(argc, argv, i, "i", "impl", v)) o.impl = v;
     else if (take(argc, argv, i, "d", "devices", v)) o.device = v;
@@ -177,7 +180,7 @@ int main(int argc, char *argv[]) {
   }
   std::string output = replaceAll(replaceAll(replaceAll(o.output, "{iter}", std::to_string(o.iterations)), "{type}", "fp32"), "{impl}", o.impl);
   try {
-    sph::cuda_impl::Solver<size_t, float, pbf::vec> solver(0.1f, std::stoi(o.device));  // h = 0.1, benchmark.cpp:160-163
+    sph::cuda_impl::Solver<size_t, float, pbf::vec> solver(0.1f, std::stoi(o.device), o.pin);  // h = 0.1, benchmark.cpp:160-163
     const float scaling = 500;  // benchmark.cpp:25
     auto [mc, param, particles] = o.scene == "dam"
         ? sph::damBreak<size_t, float, pbf::vec>(static_cast<size_t>(std::cbrt(double(o.particles)) + 0.5), o.solverIter, scaling)

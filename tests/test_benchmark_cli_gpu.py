@@ -90,3 +90,31 @@ def test_checkpoint_resume_is_bit_exact(gpu, tmp_path):
     bad = tmp_path / "bad.bin"
     bad.write_bytes(b"nonsense")
     assert run(*common, "-n", "1", "--load-state", str(bad), "-o", "").returncode != 0
+
+
+def test_pinned_caller_memory_gives_the_same_particles(gpu, tmp_path):
+    """PBF_FLAG_PIN_HOST (the benchmark driver's default, --no-pin turns it off): the library page-locks the caller's
+    array for the copies of advance().  Same bytes out, through the C ABI with pageable numpy arrays (also when the
+    array changes between calls and after an explicit unpin) and through the C++ adaptor's std::vector."""
+    from pbf_sph_b200 import FLAG_PIN_HOST
+    p, xs = scenes.dam_break(40, 3)  # 64 000 particles = 3.6 MB: above the 1 MB registration threshold
+    plain, pinned, other = xs.copy(), xs.copy(), xs.copy()
+    with Solver(scenes.H, 0) as s:
+        for _ in range(3):
+            s.advance(p, plain)
+    with Solver(scenes.H, 0, FLAG_PIN_HOST) as s:
+        s.advance(p, pinned)
+        s.advance(p, pinned)          # the same array again: the lock is reused
+        s.advance(p, other)           # another array: the lock moves
+        s.unpin_host()
+        s.advance(p, pinned)
+        del other                     # (released above: freeing is safe)
+    assert pinned.tobytes() == plain.tobytes()
+    outs = []
+    for extra in ((), ("--no-pin",)):
+        tag = "nopin" if extra else "pin"
+        out = run("--scene=dam", "--particles=64000", "--solver-iters=3", "--surface=off", "-n3", "-w2",
+                  "-o", str(tmp_path / (tag + "_{iter}")), *extra)
+        assert out.returncode == 0, out.stderr
+        outs.append((tmp_path / (tag + "_3") / "cloud.ply").read_bytes())
+    assert outs[0] == outs[1]
