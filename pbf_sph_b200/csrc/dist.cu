@@ -222,7 +222,18 @@ __global__ void ghost_mask_kernel(const uint32_t *__restrict__ keys, uint32_t n,
   const uint32_t key = i < n ? __ldg(keys + i) : 0xFFFFFFFFu;
   const bool leader = i < n && (i == 0 || __ldg(keys + i - 1) != key);
   const uint32_t lo = splits[rank], hi = splits[rank + 1];
-  unsigned leaders = __ballot_sync(0xFFFFFFFFu, leader);
+  // Most cells are deep inside the slab.  The Morton key is monotone in every coordinate, so the keys of the 5 x 5 x 5
+  // box lie between those of its two extreme corners: when both corners are ours, every cell of the box is, and the
+  // 125-cell search is not needed (exact, not a heuristic; boxes that wrap around the 10-bit grid take the search).
+  bool search = leader && key < G;
+  if (search) {
+    const uint32_t x = compact10(key), y = compact10(key >> 1), z = compact10(key >> 2);
+    if (x >= 2u && y >= 2u && z >= 2u && x <= 1021u && y <= 1021u && z <= 1021u) {
+      const uint32_t kmin = morton3(x - 2u, y - 2u, z - 2u), kmax = morton3(x + 2u, y + 2u, z + 2u);
+      search = !(kmin >= lo && kmax < hi);
+    }
+  }
+  unsigned leaders = __ballot_sync(0xFFFFFFFFu, search);
   uint32_t mine = 0;
   while (leaders) {
     const int src = __ffs(leaders) - 1;
