@@ -88,6 +88,34 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_apply_kernel(const uin
   if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
 }
 
+// Up to 8 tiles in ONE launch: a single block walks the tiles with a running carry.  The slab path scans a few
+// thousand per-block counters several times per step, right after host read-backs, where every launch is latency.
+constexpr uint64_t kScanSmall = 8ull * kScanTile;  // beyond that the serial walk loses to three parallel launches
+__global__ void __launch_bounds__(kScanThreads) scan_small_kernel(const uint32_t *in, uint64_t n, uint32_t *out,
+                                                                  uint32_t *total_out) {
+  uint32_t carry = 0;
+  for (uint64_t tile = 0; tile * kScanTile < n; ++tile) {
+    const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      v[k] = (base + k < n) ? in[base + k] : 0u;
+      s += v[k];
+    }
+    uint32_t total;
+    uint32_t run = block_excl_scan(s, &total) + carry;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (base + k < n) out[base + k] = run;
+      run += v[k];
+    }
+    carry += total;
+    __syncthreads();  // block_excl_scan's shared scratch is reused by the next tile
+  }
+  if (total_out && threadIdx.x == 0) *total_out = carry;
+}
+
 // ======================================= radix sort ============================================================
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
@@ -215,6 +243,11 @@ int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t
   const uint64_t t1 = (n + kScanTile - 1) / kScanTile;
   if (t1 == 1) {
     scan_tile_apply_kernel<<<1, kScanThreads, 0, ctx->stream>>>(in, n, nullptr, out, total_out_dev);
+    PBF_LAUNCH_CHECK(ctx);
+    return PBF_OK;
+  }
+  if (n <= kScanSmall) {
+    scan_small_kernel<<<1, kScanThreads, 0, ctx->stream>>>(in, n, out, total_out_dev);
     PBF_LAUNCH_CHECK(ctx);
     return PBF_OK;
   }
