@@ -129,7 +129,7 @@ EXPORTS = [
     "pbf_particle_count", "pbf_device_state", "pbf_grid", "pbf_debug_read", "pbf_profile_reset", "pbf_profile_read",
     "pbf_launch_count", "pbf_dist_unique_id", "pbf_dist_init", "pbf_dist_init_local", "pbf_dist_upload",
     "pbf_dist_step", "pbf_dist_download", "pbf_dist_set_replan", "pbf_dist_stats_read", "pbf_host_alloc", "pbf_host_free", "pbf_host_grid",
-    "pbf_host_plan_splits", "pbf_host_constants", "pbf_host_morton_encode", "pbf_host_morton_decode",
+    "pbf_host_plan_splits", "pbf_host_work_weights", "pbf_host_constants", "pbf_host_morton_encode", "pbf_host_morton_decode",
     "pbf_host_apply_motion",
 ]
 
@@ -190,6 +190,7 @@ def lib() -> C.CDLL:
         "pbf_host_free": ([vp], None),
         "pbf_host_grid": ([f32, P(Params), P(GridInfo)], i32),
         "pbf_host_plan_splits": ([vp, u32, u32, i32, vp], i32),
+        "pbf_host_work_weights": ([vp, u32, u32, vp], i32),
         "pbf_host_constants": ([f32, vp], None),
         "pbf_host_morton_encode": ([u32, u32, u32], u32),
         "pbf_host_morton_decode": ([u32, vp], None),

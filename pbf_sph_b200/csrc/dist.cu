@@ -547,11 +547,7 @@ int phase_plan(pbf_ctx *c) {
   // tests every particle of its 27 cells.  Fit on one device (dam-1m: 1.89 us per particle-step at 6.3 particles per
   // cell, 2.08 us at 7.4): cost ~ 4.4 + density, with the bucket's particles per key slot as the density.
   std::vector<uint64_t> h64(d->hist_buckets);
-  const double slots = (double)(1ull << d->hist_shift);
-  for (uint32_t b = 0; b < d->hist_buckets; ++b) {
-    const bool beyond_grid = b + 1 == d->hist_buckets;  // the last bucket collects every key >= G: no density there
-    h64[b] = (uint64_t)h32[b] * (uint64_t)(4.4 * slots + (beyond_grid ? 0.0 : (double)h32[b]));
-  }
+  pbf_host_work_weights(h32.data(), d->hist_buckets, d->hist_shift, h64.data());
   d->splits.assign(d->world + 1, 0);
   plan_splits(h64.data(), d->hist_buckets, d->hist_shift, d->world, d->splits.data());
   PBF_CUDA(c, cudaMemcpyAsync(d->d_splits.p, d->splits.data(), (d->world + 1) * 4, cudaMemcpyHostToDevice, c->stream));
@@ -1038,6 +1034,16 @@ int pbf_dist_stats_read(pbf_ctx *ctx, pbf_dist_stats *out) {
   *out = ctx->dist->stats;
   out->ghost_ring1 = ctx->mc_total_host[1];
   out->boundary = ctx->mc_total_host[2];
+  return PBF_OK;
+}
+
+int pbf_host_work_weights(const uint32_t *bucket_hist, uint32_t n_buckets, uint32_t shift, uint64_t *weights) {
+  if (!bucket_hist || !weights || n_buckets == 0 || shift > 30) return PBF_ERR_INVALID;
+  const double slots = (double)(1ull << shift);  // key slots (cells) per bucket
+  for (uint32_t b = 0; b < n_buckets; ++b) {
+    const bool beyond_grid = b + 1 == n_buckets;  // the last bucket collects every key >= G: no density there
+    weights[b] = (uint64_t)bucket_hist[b] * (uint64_t)(4.4 * slots + (beyond_grid ? 0.0 : (double)bucket_hist[b]));
+  }
   return PBF_OK;
 }
 

@@ -35,6 +35,28 @@ def test_plan_splits_balances_and_tiles_key_space():
         assert max(owned) <= hist.sum() / world + hist.max()
 
 
+def test_work_weights_move_the_split_towards_the_dense_half():
+    """The slab splits balance density-weighted work (pbf_host_work_weights), not particle counts: with a dense and a
+    sparse half holding the same number of particles, the dense half is the heavier one, so the split moves into it."""
+    shift, per_bucket = 3, 8
+    hist = np.zeros(513, np.uint32)          # 512 buckets of 8 cells + the bucket of everything >= G
+    hist[:128] = 12 * per_bucket             # dense quarter: 12 particles per cell
+    hist[128:512] = 4 * per_bucket           # sparse three quarters: 4 per cell — the same particle count in total
+    hist[512] = 50                           # particles outside the grid: counted, but no density
+    w = np.zeros(len(hist), np.uint64)
+    assert capi.lib().pbf_host_work_weights(hist.ctypes.data, len(hist), shift, w.ctypes.data) == 0
+    slots = 1 << shift
+    assert np.array_equal(w[:512], hist[:512].astype(np.uint64) * (np.uint64(int(4.4 * slots)) + hist[:512].astype(np.uint64)))
+    assert w[512] == 50 * int(4.4 * slots)
+    by_count = plan(hist.astype(np.uint64), shift, 2)[1] >> shift
+    by_work = plan(w, shift, 2)[1] >> shift
+    assert by_count == 129                   # half of the particles: the dense quarter (+ one bucket of rounding)
+    assert by_work < by_count                # half of the WORK is reached earlier, inside the dense quarter
+    dense_cost, sparse_cost = 128 * 96 * (35 + 96), 384 * 32 * (35 + 32)
+    assert abs(int(w[:by_work].sum()) - (dense_cost + sparse_cost + int(w[512])) / 2) <= w[:512].max()
+    assert capi.lib().pbf_host_work_weights(None, 4, 3, w.ctypes.data) != 0
+
+
 def test_plan_splits_degenerate_inputs():
     assert list(plan([0, 0, 0, 0], 0, 2)) == [0, 0, 1 << 30]            # no particles at all
     assert list(plan([10, 0, 0, 0], 4, 4)) == [0, 16, 16, 16, 1 << 30]  # everything in one bucket
