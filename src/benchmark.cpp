@@ -255,6 +255,7 @@ int main(int argc, char *argv[]) {
               << "Query answers        :" << [&] { std::string q; for (const auto &a : result.queries) q += " " + std::to_string(a.id) + ":" + std::to_string(a.neighbours.size()); return q.empty() ? std::string(" none") : q; }() << "\n"
               << "Particle-iterations/s: " << double(particles.size()) * double(o.solverIter) * double(o.iterations) / seconds << "\n"
               << std::endl;
+    solver.unpin();  // the particle vector goes out of scope before the solver does: release its page-lock first
     if (!o.saveState.empty()) saveState(particles, o.saveState);
     save(result, particles, output);
     std::cout << "Results flushed." << std::endl;
