@@ -10,6 +10,12 @@
 // The whole sph::Scene is honoured on the device (scene.cu): sources emit and drains remove on the resident arrays
 // (ompsph.hpp:91-120), wells pull inside the prediction (:141-148), queries are answered from the step's cell table
 // (:167-186).
+//
+// Several devices: Solver(h, {0, 1, 2, 3}) — the reference's `-d/--devices` is a list (args.cpp:20-23, args.hpp:46) —
+// runs the step slab-decomposed along the Z-curve over those GPUs (csrc/dist.cu: one rank per device inside this
+// process, ghost layers exchanged once per solver iteration) and returns the very particles, in the very order, one
+// device returns.  Scene dynamics and the surface are single-device features for now: with several devices a
+// non-empty Scene or config.surface raises std::runtime_error.
 #pragma once
 
 #include <algorithm>
@@ -34,7 +40,8 @@ template <typename T, typename N, template <size_t, typename> typename V> class 
   static_assert(sizeof(P) == sizeof(pbf_particle) && alignof(P) == alignof(pbf_particle), "Particle layout");
   static_assert(sizeof(V<3, N>) == 12 && sizeof(V<4, N>) == 16, "vector layout");
 
-  pbf_ctx *ctx = nullptr;
+  pbf_ctx *ctx = nullptr;            // rank 0 (the only context on one device)
+  std::vector<pbf_ctx *> ranks;      // every context, rank order
   const N h;
 
   [[noreturn]] void raise(const char *where) const {
@@ -46,12 +53,32 @@ public:
   // the copies of advance() run at the PCIe rate instead of through the runtime's pageable staging.  Safe whenever the
   // caller keeps its vector alive between calls, as both reference drivers do (benchmark.cpp:22-58, visualise.cpp:85-109);
   // this adaptor releases the lock itself before it grows the vector.  Call unpin() before freeing the vector early.
-  explicit Solver(N h, int device = 0, bool pinCallerMemory = false) : h(h) {
-    if (pbf_create(&ctx, h, device) != PBF_OK) raise("pbf_create");
-    if (pinCallerMemory && pbf_set_flags(ctx, PBF_FLAG_PIN_HOST) != PBF_OK) raise("pbf_set_flags");
+  explicit Solver(N h, int device = 0, bool pinCallerMemory = false) : Solver(h, std::vector<int>{device}, pinCallerMemory) {}
+  // One slab rank per entry of `devices` (ordinals may repeat: several ranks then share a GPU).
+  Solver(N h, const std::vector<int> &devices, bool pinCallerMemory = false) : h(h) {
+    if (devices.empty()) throw std::runtime_error("sph::cuda_impl::Solver: empty device list");
+    try {
+      for (int dev : devices) {
+        pbf_ctx *c = nullptr;
+        if (pbf_create(&c, h, dev) != PBF_OK) {
+          const std::string why = pbf_last_error(nullptr);
+          throw std::runtime_error("sph::cuda_impl::Solver: pbf_create: " + why);
+        }
+        ranks.push_back(c);
+      }
+      ctx = ranks[0];
+      if (pinCallerMemory && pbf_set_flags(ctx, PBF_FLAG_PIN_HOST) != PBF_OK) raise("pbf_set_flags");
+      if (ranks.size() > 1 && pbf_dist_init_local(ranks.data(), int(ranks.size())) != PBF_OK) raise("pbf_dist_init_local");
+    } catch (...) {
+      for (pbf_ctx *c : ranks) pbf_destroy(c);
+      throw;
+    }
   }
   void unpin() { pbf_unpin_host(ctx); }
-  ~Solver() override { pbf_destroy(ctx); }
+  size_t deviceCount() const { return ranks.size(); }
+  ~Solver() override {
+    for (pbf_ctx *c : ranks) pbf_destroy(c);
+  }
   Solver(const Solver &) = delete;
   Solver &operator=(const Solver &) = delete;
 
@@ -73,6 +100,7 @@ public:
 
   sph::Result<T, N, V> advance(const sph::SphParams<T, N, V> &config, const sph::Scene<T, N, V> &scene,
                                std::vector<P> &xs) override {
+    if (ranks.size() > 1) return advanceSlabs(config, scene, xs);
     // sph::Scene -> pbf_scene (plain arrays; the library copies them)
     std::vector<pbf_well> wells;
     std::vector<pbf_source> sources;
@@ -123,6 +151,21 @@ public:
       r.queries.push_back({scene.queries[i].id, scene.queries[i].point, std::vector<T>(ids.begin(), ids.end())});
     }
     return r;
+  }
+
+private:
+  sph::Result<T, N, V> advanceSlabs(const sph::SphParams<T, N, V> &config, const sph::Scene<T, N, V> &scene, std::vector<P> &xs) {
+    if (!scene.wells.empty() || !scene.sources.empty() || !scene.drains.empty() || !scene.queries.empty())
+      throw std::runtime_error("sph::cuda_impl::Solver: a non-empty Scene needs a single device");
+    if (xs.empty()) {
+      std::cout << "Particles depleted" << std::endl;  // ompsph.hpp:122-126
+      std::this_thread::sleep_for(std::chrono::milliseconds(5));
+      return {};
+    }
+    const pbf_params p = toParams(config);
+    uint64_t nv = 0;
+    if (pbf_dist_advance_host(ctx, &p, reinterpret_cast<pbf_particle *>(xs.data()), xs.size(), &nv) != PBF_OK) raise("advance");
+    return {};
   }
 };
 

@@ -146,7 +146,11 @@ typedef enum pbf_tap {
   PBF_TAP_RHO = 7,         /* f32[n]  density of the LAST solver iteration (ompsph.hpp:227) */
   PBF_TAP_IDS = 8,         /* u64[n] */
   PBF_TAP_MC_FIELD = 9,    /* f32[4*L] lattice (value, normal.xyz), index3d order (ompsph.hpp:350-354) */
-  PBF_TAP_MC_COLOUR = 10   /* f32[4*L] lattice colour (ompsph.hpp:355) */
+  PBF_TAP_MC_COLOUR = 10,  /* f32[4*L] lattice colour (ompsph.hpp:355) */
+  /* u32[n]  in-radius candidates incl. self as the PRODUCTION search counted them: the hit count of the neighbour list
+   * the lambda pass of the FIRST solver iteration wrote (csrc/neighbour_list.cu), i.e. on the same predicted positions as
+   * PBF_TAP_NBR_COUNT.  Needs PBF_FLAG_DEBUG_COUNTS; not available under PBF_FLAG_GLOBAL_NEIGHBOURS (no list). */
+  PBF_TAP_LIST_HITS = 11
 } pbf_tap;
 
 /* Kernel families timed under PBF_FLAG_PROFILE.  ms are accumulated since the last pbf_profile_reset. */
@@ -229,6 +233,10 @@ int pbf_device_state(pbf_ctx *ctx, void **pos4, void **vel4, void **col4, void *
 /* ---- introspection for parity tests and the bench ------------------------------------------------ */
 int pbf_grid(pbf_ctx *ctx, pbf_grid_info *out);
 int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes);
+/* Parity tests only: depth of the per-iteration neighbour list (hits kept per particle; 192 by default, 96 is the other
+ * compiled depth).  A particle with more hits than the depth takes the one-pass 27-cell walk in both solver passes; the
+ * tests use the shallow list to drive that path on moderately dense clumps. */
+int pbf_debug_set_list_capacity(pbf_ctx *ctx, uint32_t hits);
 int pbf_profile_reset(pbf_ctx *ctx);
 int pbf_profile_read(pbf_ctx *ctx, pbf_profile *out);
 /* Number of kernel launches issued by this context since creation. */
@@ -253,6 +261,12 @@ int pbf_dist_upload(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n);
 int pbf_dist_step(pbf_ctx *ctx, const pbf_params *params);
 /* Owned particles of this rank, Z-sorted (concatenating ranks 0..world-1 gives the global Z order). */
 int pbf_dist_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_t *n_out);
+/* sph::Solver::advance (sph.hpp:119-125) on a LOCAL group — what sph::cuda_impl::Solver(h, {dev0, dev1, ...}) calls:
+ * the caller's array is cut into one block per rank, uploaded, stepped by the whole group and returned in the global
+ * Z-sorted order (ompsph.hpp:479-481), exactly as pbf_advance_host does on one device (same particles, same order,
+ * bit-identical values).  `ctx` is any member of the group; PBF_FLAG_PIN_HOST is read from rank 0's flags. */
+int pbf_dist_advance_host(pbf_ctx *ctx, const pbf_params *params, pbf_particle *xs, uint64_t n,
+                          uint64_t *n_mesh_vertices);
 /* Re-plan the key splits from a global key histogram every `steps` steps (default 4; 0 = only at the first step). */
 int pbf_dist_set_replan(pbf_ctx *ctx, uint32_t steps);
 typedef struct pbf_dist_stats {

@@ -31,7 +31,7 @@ FLAG_VORTICITY = 1 << 5
 FLAG_PIN_HOST = 1 << 6  # page-lock the caller's array in the drop-in call (see include/pbf_cuda.h for the contract)
 
 TAP_KEYS_INPUT, TAP_PERM, TAP_KEYS_SORTED, TAP_CELL_TABLE, TAP_CAND_COUNT, TAP_NBR_COUNT = range(6)
-TAP_LAMBDA, TAP_RHO, TAP_IDS, TAP_MC_FIELD, TAP_MC_COLOUR = range(6, 11)
+TAP_LAMBDA, TAP_RHO, TAP_IDS, TAP_MC_FIELD, TAP_MC_COLOUR, TAP_LIST_HITS = range(6, 12)
 
 PHASES = ["predict_key", "sort", "reorder", "cell_table", "diffuse", "lambda", "delta", "finalise", "mc_field",
           "mc_count_scan", "mc_emit", "pack", "halo"]
@@ -126,9 +126,9 @@ EXPORTS = [
     "pbf_advance_host", "pbf_advance_scene_host", "pbf_unpin_host", "pbf_query_result", "pbf_set_scene", "pbf_mesh_download",
     "pbf_mesh_device", "pbf_upload",
     "pbf_step", "pbf_sync", "pbf_download",
-    "pbf_particle_count", "pbf_device_state", "pbf_grid", "pbf_debug_read", "pbf_profile_reset", "pbf_profile_read",
+    "pbf_particle_count", "pbf_device_state", "pbf_grid", "pbf_debug_read", "pbf_debug_set_list_capacity", "pbf_profile_reset", "pbf_profile_read",
     "pbf_launch_count", "pbf_dist_unique_id", "pbf_dist_init", "pbf_dist_init_local", "pbf_dist_upload",
-    "pbf_dist_step", "pbf_dist_download", "pbf_dist_set_replan", "pbf_dist_stats_read", "pbf_host_alloc", "pbf_host_free", "pbf_host_grid",
+    "pbf_dist_step", "pbf_dist_advance_host", "pbf_dist_download", "pbf_dist_set_replan", "pbf_dist_stats_read", "pbf_host_alloc", "pbf_host_free", "pbf_host_grid",
     "pbf_host_plan_splits", "pbf_host_work_weights", "pbf_host_constants", "pbf_host_morton_encode", "pbf_host_morton_decode",
     "pbf_host_apply_motion",
 ]
@@ -175,6 +175,7 @@ def lib() -> C.CDLL:
         "pbf_device_state": ([vp, P(vp), P(vp), P(vp), P(vp)], i32),
         "pbf_grid": ([vp, P(GridInfo)], i32),
         "pbf_debug_read": ([vp, i32, vp, u64], i32),
+        "pbf_debug_set_list_capacity": ([vp, u32], i32),
         "pbf_profile_reset": ([vp], i32),
         "pbf_profile_read": ([vp, P(Profile)], i32),
         "pbf_launch_count": ([vp], u64),
@@ -184,6 +185,7 @@ def lib() -> C.CDLL:
         "pbf_dist_set_replan": ([vp, u32], i32),
         "pbf_dist_upload": ([vp, vp, u64], i32),
         "pbf_dist_step": ([vp, P(Params)], i32),
+        "pbf_dist_advance_host": ([vp, P(Params), vp, u64, P(u64)], i32),
         "pbf_dist_download": ([vp, vp, u64, P(u64)], i32),
         "pbf_dist_stats_read": ([vp, P(DistStats)], i32),
         "pbf_host_alloc": ([u64], vp),

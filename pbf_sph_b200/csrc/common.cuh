@@ -186,6 +186,7 @@ struct pbf_ctx {
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;
+  int diffuse_blocks_per_sm = 0;  // diffuse_tiled.cu: resident blocks per SM on THIS context's device (0 = not set up yet)
 
   uint64_t n = 0;  // resident particles
   bool have_state = false;
@@ -201,6 +202,7 @@ struct pbf_ctx {
   pbf::DevBuf<uint32_t> table;
   pbf::DevBuf<uint32_t> scan_tmp;
   pbf::DevBuf<uint32_t> cand_count, nbr_count;
+  pbf::DevBuf<uint32_t> list_hits;  // PBF_TAP_LIST_HITS: the production list's hit counts after the first lambda pass
   pbf::DevBuf<float> rho;
   pbf::DevBuf<pbf_particle> aos;  // staging for the drop-in path
   pbf_particle *host_pinned = nullptr;
@@ -220,17 +222,8 @@ struct pbf_ctx {
   // per-iteration neighbour list: nl[k * nl_stride + particle] = k-th in-radius candidate, nl_count[particle] = hits
   pbf::DevBuf<uint32_t> nl, nl_count;
   uint32_t nl_stride = 0;
-  int list_cap = 192;     // hits kept per particle in the neighbour list: kListWide, or 96 / 64 via PBF_LIST_CAP (A/B runs)
+  int list_cap = 192;     // hits kept per particle in the neighbour list: kListWide (or kListMax via pbf_debug_set_list_capacity)
   uint32_t nl_cap = 96;   // the capacity the current list was written with (neighbour_list.cu)
-  // per-step plan of the warp-per-cell search (cell_search.cu): cells to search, their targets and flat candidate lists
-  pbf::DevBuf<uint32_t> plan_heads, plan_cand;
-  pbf::DevBuf<uint4> plan_info;
-  bool plan_valid = false;  // cleared whenever the cell table is rebuilt
-  uint32_t plan_first = 0, plan_count = 0, plan_want = 0;
-  const uint32_t *plan_role = nullptr;
-  // 0: thread-per-particle search walking the cell table (neighbour_list.cu, the production form);
-  // 1: warp-per-cell search over the per-step plan (cell_search.cu, PBF_SEARCH=cells).  Both write the same lists.
-  int search_mode = 0;
 
   pbf_scene_state scene;
 
@@ -307,17 +300,11 @@ int launch_lambda_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uin
 int launch_delta_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
                         const uint32_t *table, const float4 *pstar_in, float4 *pstar_out);
 // neighbour-list kernels (neighbour_list.cu): the production lambda/delta passes
-constexpr uint32_t kListMax = 96;    // hits stored per particle by the warp-per-cell search (its staged lists)
-constexpr uint32_t kListWide = 192;  // ... and by the production search; beyond that the particle takes the one-pass path
+constexpr uint32_t kListMax = 96;    // list depth above 22 M particles per device (32-bit list indexing), and the A/B depth of the tests
+constexpr uint32_t kListWide = 192;  // production depth; a particle with more hits takes the one-pass path in both passes
 int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                        const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
                        const uint32_t *role = nullptr, uint32_t want = 0);
-// per-step search plan (cell_search.cu): ctx->plan_* for the cells of [first, first + count) whose role matches
-int ensure_search_plan(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                       const uint32_t *role, uint32_t want);
-// warp-per-cell neighbour search (cell_search.cu): fills ctx->nl / ctx->nl_count for the matching particles
-int launch_search_cells(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                        const float4 *pstar_in, uint32_t stride, const uint32_t *role, uint32_t want);
 // role != nullptr: particle a is processed only when role[a] & want (multi-GPU: ring-1 / boundary / interior, dist.cu)
 int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                       const float4 *pstar_in, float4 *pstar_out, const uint32_t *role = nullptr, uint32_t want = 0);
@@ -338,6 +325,10 @@ int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t
 int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col);
 
 void dist_release(pbf_ctx *ctx);  // dist.cu
+// host <-> device plumbing of the drop-in calls (context.cu), shared with the multi-device drop-in call (dist.cu)
+int upload_device(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n);  // async H2D + unpack on ctx->stream; sets ctx->n
+void host_pin(pbf_ctx *ctx, void *p, size_t bytes);                   // PBF_FLAG_PIN_HOST
+void host_unpin(pbf_ctx *ctx);
 // scene dynamics (scene.cu)
 int scene_set(pbf_ctx *ctx, const pbf_scene *scene);
 int scene_edit_particles(pbf_ctx *ctx, const pbf_params &p);  // sources, then drains, on the resident particles

@@ -14,6 +14,8 @@
 
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a profiler is attached
+
 #include "common.cuh"
 
 namespace pbf {
@@ -94,7 +96,14 @@ void host_step_const(float h, const pbf_params &p, const pbf_grid_info &g, uint3
 }
 
 // ---- profiling ---------------------------------------------------------------------------------------------------
+// NVTX range names = the reference's stopwatch phases (ompsph.hpp:89,130,157,161,188,209,252,279,359,399,479), so a
+// timeline of this backend reads like the reference's own "advance" breakdown.
+static const char *const kPhaseNames[PBF_PH_COUNT] = {
+    "advect+copy (predict_key)", "sortz (radix sort)", "sortz (reorder)", "gridtable", "sph-diffuse", "sph-lambda", "sph-delta",
+    "sph-finalise", "mc-field", "mc_psum", "gpu_mc", "write back", "halo", "", "", ""};
+
 PhaseScope::PhaseScope(pbf_ctx *c, int ph) : ctx(c), phase(ph), slot(-1) {
+  nvtxRangePushA(kPhaseNames[ph]);
   if (!(ctx->flags & PBF_FLAG_PROFILE)) return;
   if (!ctx->ev_created) {
     for (int i = 0; i < pbf_ctx::kMaxEv; ++i) cudaEventCreate(&ctx->ev[i]);
@@ -108,6 +117,7 @@ PhaseScope::PhaseScope(pbf_ctx *c, int ph) : ctx(c), phase(ph), slot(-1) {
   cudaEventRecord(ctx->ev[slot], ctx->stream);
 }
 PhaseScope::~PhaseScope() {
+  nvtxRangePop();
   if (slot < 0) return;
   cudaEventRecord(ctx->ev[slot + 1], ctx->stream);
   ctx->prof.launches[phase] += ctx->launches - ctx->ev_launch0[slot];
@@ -152,8 +162,15 @@ static int validate(pbf_ctx *ctx, const pbf_params *p) {
   return PBF_OK;
 }
 
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 static int step_device(pbf_ctx *ctx, const pbf_params &p) {
+  NvtxRange whole("advance");  // ompsph.hpp:89
   if (!ctx->scene.empty()) {
+    NvtxRange r("source+drain");  // ompsph.hpp:91
     PBF_TRY(validate(ctx, &p));
     PBF_TRY(scene_edit_particles(ctx, p));  // sources, then drains (ompsph.hpp:91-120)
   }
@@ -215,6 +232,10 @@ static int step_device(pbf_ctx *ctx, const pbf_params &p) {
   ctx->cur_col ^= 1;
   for (uint64_t it = 0; it < p.iteration; ++it) {
     PBF_TRY(solver_lambda(ctx, 0, n, ctx->pstar[0].p, ctx->pstar[1].p, it + 1 == p.iteration ? ctx->rho.p : nullptr));
+    if (it == 0 && (ctx->flags & PBF_FLAG_DEBUG_COUNTS) && tiled) {  // PBF_TAP_LIST_HITS
+      PBF_CUDA(ctx, ctx->list_hits.reserve(n));
+      PBF_CUDA(ctx, cudaMemcpyAsync(ctx->list_hits.p, ctx->nl_count.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     PBF_TRY(solver_delta(ctx, 0, n, ctx->pstar[1].p, ctx->pstar[0].p));
   }
   PBF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
@@ -230,7 +251,7 @@ static int step_device(pbf_ctx *ctx, const pbf_params &p) {
   return PBF_OK;
 }
 
-static int upload_device(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n) {
+int upload_device(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n) {
   ctx->n = 0;
   ctx->have_state = false;
   if (n >= 0xFFFFFFF0ull) return fail(ctx, PBF_ERR_INVALID, "n", "more than 2^32 particles on one device");
@@ -252,7 +273,7 @@ static int upload_device(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n) {
 }
 
 // PBF_FLAG_PIN_HOST: page-lock the caller's array so that the H2D / D2H of the drop-in call are DMA transfers.
-static void host_unpin(pbf_ctx *ctx) {
+void host_unpin(pbf_ctx *ctx) {
   if (!ctx->pin_base) return;
   cudaHostUnregister(ctx->pin_base);
   cudaGetLastError();  // a caller that freed the array first has broken the contract; nothing to unwind here
@@ -260,7 +281,7 @@ static void host_unpin(pbf_ctx *ctx) {
   ctx->pin_bytes = 0;
 }
 
-static void host_pin(pbf_ctx *ctx, void *p, size_t bytes) {
+void host_pin(pbf_ctx *ctx, void *p, size_t bytes) {
   if (ctx->pin_base == p && bytes <= ctx->pin_bytes) return;  // the array we already hold
   host_unpin(ctx);
   if (!p || bytes < (1u << 20)) return;  // small arrays: registration costs more than it saves
@@ -324,8 +345,6 @@ int pbf_create(pbf_ctx **out, float h, int device) {
     return PBF_ERR_CUDA;
   }
   ctx->own_stream = true;
-  if (const char *e = getenv("PBF_LIST_CAP")) ctx->list_cap = atoi(e) == 64 ? 64 : (atoi(e) == 96 ? (int)kListMax : (int)kListWide);
-  if (const char *e = getenv("PBF_SEARCH")) ctx->search_mode = (e[0] == 'c') ? 1 : 0;
   *out = ctx;
   return PBF_OK;
 }
@@ -349,11 +368,10 @@ void pbf_destroy(pbf_ctx *ctx) {
   }
   ctx->key_in.release(); ctx->key_a.release(); ctx->key_b.release(); ctx->idx_a.release(); ctx->idx_b.release();
   ctx->sort_hist.release(); ctx->sort_tmp.release(); ctx->table.release(); ctx->scan_tmp.release();
-  ctx->cand_count.release(); ctx->nbr_count.release(); ctx->rho.release(); ctx->aos.release();
+  ctx->cand_count.release(); ctx->nbr_count.release(); ctx->list_hits.release(); ctx->rho.release(); ctx->aos.release();
   ctx->mc_pn.release(); ctx->mc_c.release(); ctx->mc_count.release(); ctx->mc_offset.release();
   ctx->mesh_vs.release(); ctx->mesh_ns.release(); ctx->mesh_cs.release();
   ctx->blk_list.release(); ctx->blk_info.release(); ctx->nl.release(); ctx->nl_count.release();
-  ctx->plan_heads.release(); ctx->plan_cand.release(); ctx->plan_info.release();
   if (ctx->flag_dev) cudaFree(ctx->flag_dev);
   if (ctx->flag_host) cudaFreeHost(ctx->flag_host);
   if (ctx->mc_total_dev) cudaFree(ctx->mc_total_dev);
@@ -551,6 +569,7 @@ int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes) {
     case PBF_TAP_CELL_TABLE: src = ctx->table.p; bytes = (uint64_t)ctx->grid.grid_table_n * 4; break;
     case PBF_TAP_CAND_COUNT: src = ctx->cand_count.p; bytes = n * 4; break;
     case PBF_TAP_NBR_COUNT: src = ctx->nbr_count.p; bytes = n * 4; break;
+    case PBF_TAP_LIST_HITS: src = ctx->list_hits.p; bytes = n * 4; break;
     case PBF_TAP_LAMBDA: src = ctx->pstar[1].p; bytes = n * 4; strided_w = true; break;
     case PBF_TAP_RHO: src = ctx->rho.p; bytes = n * 4; break;
     case PBF_TAP_IDS: src = ctx->ids[ctx->cur].p; bytes = n * 8; break;
@@ -565,6 +584,13 @@ int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes) {
   else
     PBF_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PBF_OK;
+}
+
+int pbf_debug_set_list_capacity(pbf_ctx *ctx, uint32_t hits) {
+  PBF_ENTER(ctx);
+  if (hits != kListMax && hits != kListWide) return fail(ctx, PBF_ERR_INVALID, "pbf_debug_set_list_capacity", "96 or 192");
+  ctx->list_cap = (int)hits;
   return PBF_OK;
 }
 

@@ -207,12 +207,15 @@ int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32
                                                                             ctx->blk_info.p);
     PBF_LAUNCH_CHECK(ctx);
   }
-  static int per_sm = 0;
-  if (per_sm == 0) {
+  // Function attributes are per device: the opt-in to > 48 KB of dynamic shared memory and the occupancy are set up once
+  // per CONTEXT (a process may drive several devices: pbf_dist_init_local with distinct ordinals, or two Solvers).
+  if (ctx->diffuse_blocks_per_sm == 0) {
+    int per_sm = 0;
     PBF_CUDA(ctx, cudaFuncSetAttribute(diffuse_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     PBF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, diffuse_tiled_kernel, kThreads, sizeof(Smem)));
-    if (per_sm < 1) per_sm = 1;
+    ctx->diffuse_blocks_per_sm = per_sm < 1 ? 1 : per_sm;
   }
+  const int per_sm = ctx->diffuse_blocks_per_sm;
   TiledArgs g{keys_sorted, table, col_in, col_out, ctx->blk_list.p, ctx->blk_info.p, ctx->blk_info.p + 1};
   diffuse_tiled_kernel<<<(unsigned)(ctx->sm_count * per_sm), kThreads, sizeof(Smem), ctx->stream>>>(ctx->sc, g);
   PBF_LAUNCH_CHECK(ctx);

@@ -128,6 +128,7 @@ struct pbf_dist_state {
   DevBuf<unsigned long long> sb_id;
   DevBuf<uint32_t> sb_key;
   uint32_t *h_pinned = nullptr;  // (world + 1) * (world + 2) + 64 words
+  std::vector<uint64_t> last_counts;  // pbf_dist_advance_host: particles every rank returned from the previous call
   std::vector<Msg> msgs;
   pbf_dist_stats stats{};
   void release() {
@@ -1024,6 +1025,68 @@ int pbf_dist_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_
                           ctx->col[ctx->cur_col].p + off, ctx->ids[ctx->cur].p + off));
   PBF_CUDA(ctx, cudaMemcpyAsync(xs, ctx->aos.p, ctx->n * sizeof(pbf_particle), cudaMemcpyDeviceToHost, ctx->stream));
   PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PBF_OK;
+}
+
+// sph::Solver::advance over a LOCAL group (the multi-device form of pbf_advance_host): the caller's array is cut into
+// one contiguous block per rank (the previous call's per-rank counts when the particle count is unchanged, so that
+// a returning array lands on the ranks that own it; equal blocks otherwise — the first step migrates anyway), uploaded
+// on every rank's stream at once, stepped, and read back in rank order, which is the global Z order (ompsph.hpp:479-481).
+int pbf_dist_advance_host(pbf_ctx *ctx, const pbf_params *params, pbf_particle *xs, uint64_t n, uint64_t *n_mesh_vertices) {
+  if (n_mesh_vertices) *n_mesh_vertices = 0;
+  if (!ctx || !ctx->dist) return fail(ctx, PBF_ERR_STATE, "pbf_dist_advance_host", "pbf_dist_init_local first");
+  if (!ctx->dist->local_mode)
+    return fail(ctx, PBF_ERR_STATE, "pbf_dist_advance_host", "one-process groups only (pbf_dist_init_local); NCCL ranks use pbf_dist_upload / step / download");
+  if (!params) return fail(ctx, PBF_ERR_INVALID, "params", "NULL");
+  if (n == 0) return PBF_OK;  // ompsph.hpp:122-126
+  if (!xs) return fail(ctx, PBF_ERR_INVALID, "xs", "NULL");
+  std::vector<pbf_ctx *> &L = *ctx->dist->group;
+  const size_t W = L.size();
+  D *d0 = L[0]->dist;
+  std::vector<uint64_t> cnt(W);
+  uint64_t had = 0;
+  for (uint64_t c : d0->last_counts) had += c;
+  if (d0->last_counts.size() == W && had == n) cnt = d0->last_counts;
+  else for (size_t r = 0; r < W; ++r) cnt[r] = (n * (r + 1)) / W - (n * r) / W;
+  if (L[0]->flags & PBF_FLAG_PIN_HOST) {
+    PBF_CUDA(L[0], cudaSetDevice(L[0]->device));
+    host_pin(L[0], xs, (size_t)n * sizeof(pbf_particle));
+  }
+  uint64_t off = 0;
+  for (size_t r = 0; r < W; ++r) {
+    pbf_ctx *c = L[r];
+    PBF_CUDA(c, cudaSetDevice(c->device));
+    c->dist->own_off = 0;
+    PBF_TRY(upload_device(c, xs + off, cnt[r]));
+    off += cnt[r];
+  }
+  for (pbf_ctx *c : L) {
+    PBF_CUDA(c, cudaSetDevice(c->device));
+    PBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->n && *c->flag_host) {
+      for (pbf_ctx *q : L) { q->n = 0; q->have_state = false; }
+      return fail(ctx, PBF_ERR_INVALID, "xs", "Obstacle particles are not supported (the reference OMP backend drops them)");
+    }
+  }
+  PBF_TRY(pbf_dist_step(ctx, params));
+  off = 0;
+  for (size_t r = 0; r < W; ++r) {  // every rank's D2H is enqueued before any is waited for
+    pbf_ctx *c = L[r];
+    PBF_CUDA(c, cudaSetDevice(c->device));
+    cnt[r] = c->n;
+    if (off + c->n > n) return fail(ctx, PBF_ERR_STATE, "pbf_dist_advance_host", "particle count changed");
+    if (c->n) {
+      const uint32_t o = c->dist->own_off;
+      PBF_CUDA(c, c->aos.reserve(c->n + 1));
+      PBF_TRY(launch_pack_aos(c, c->aos.p, c->n, c->pos[c->cur].p + o, c->vel[c->cur].p + o, c->col[c->cur_col].p + o,
+                              c->ids[c->cur].p + o));
+      PBF_CUDA(c, cudaMemcpyAsync(xs + off, c->aos.p, c->n * sizeof(pbf_particle), cudaMemcpyDeviceToHost, c->stream));
+    }
+    off += c->n;
+  }
+  if (off != n) return fail(ctx, PBF_ERR_STATE, "pbf_dist_advance_host", "particle count changed");
+  PBF_TRY(sync_all(L));
+  d0->last_counts = cnt;
   return PBF_OK;
 }
 

@@ -229,57 +229,11 @@ __global__ void __launch_bounds__(kBlock, 8) delta_list_kernel(StepConst c, uint
   pstar_out[a] = acc.finish(c, pa);
 }
 
-// Phase 2 alone, for lists written by the warp-per-cell search (cell_search.cu): the density / gradient sums over
-// the hits, in list (= the reference's visiting) order.
-template <bool kStrict, int kCap>
-__global__ void __launch_bounds__(kBlock) lambda_sums_kernel(StepConst c, uint32_t first, uint32_t count,
-                                                             const uint32_t *__restrict__ keys,
-                                                             const uint32_t *__restrict__ table,
-                                                             const float4 *__restrict__ pos_mass,
-                                                             const float4 *__restrict__ pstar_in,
-                                                             float4 *__restrict__ pstar_out, float *__restrict__ rho_out,
-                                                             const uint32_t *__restrict__ nl, uint32_t stride,
-                                                             const uint32_t *__restrict__ n_hits,
-                                                             const uint32_t *__restrict__ role, uint32_t want) {
-  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
-  if (t >= count) return;
-  const uint32_t a = first + t;
-  if (role && !(__ldg(role + a) & want)) return;
-  const float4 pa = ldg4(pstar_in + a);
-  const float mass = __ldg(&pos_mass[a].w);
-  const uint32_t k = __ldg(n_hits + a);
-  LambdaAcc<kStrict> acc;
-  acc.init();
-  acc.set_mass(mass);
-  if (k <= (uint32_t)kCap) {
-    sum_over_hits<8>(acc, c, pa, pstar_in, nl + a, stride, k, a);
-  } else {
-    for_each_candidate(__ldg(keys + a), c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
-  }
-  float rho;
-  const float lambda = acc.finish(c, mass, rho);
-  pstar_out[a] = make_float4(pa.x, pa.y, pa.z, lambda);
-  if (rho_out) rho_out[a] = rho;
-}
-
 template <int kCap> int launch_lambda_cap(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
                                           const uint32_t *table, const float4 *pos_mass, const float4 *pstar_in,
                                           float4 *pstar_out, float *rho_out, uint32_t stride, const uint32_t *role,
                                           uint32_t want) {
   uint32_t *nl4 = ctx->nl.p;
-  if (ctx->search_mode == 1) {  // warp-per-cell search (PBF_SEARCH=cells), then the sums over its lists
-    PBF_TRY(launch_search_cells(ctx, first, count, keys_sorted, table, pstar_in, stride, role, want));
-    if (ctx->flags & PBF_FLAG_STRICT_FP)
-      lambda_sums_kernel<true, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-          ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, ctx->nl_count.p,
-          role, want);
-    else
-      lambda_sums_kernel<false, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-          ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, ctx->nl_count.p,
-          role, want);
-    PBF_LAUNCH_CHECK(ctx);
-    return PBF_OK;
-  }
   if (ctx->flags & PBF_FLAG_STRICT_FP)
     lambda_list_kernel<true, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
         ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride,
@@ -317,18 +271,16 @@ int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint3
   // Rows cost address space, not bandwidth (a row is touched only by particles with that many hits), so the thread-per-
   // particle search keeps up to kListWide hits: while a dam break splashes, particles clamped onto the walls pile up
   // (dam-1m after 30 steps: 431 particles with 97..229 neighbours) and every one that overflows drags its block through
-  // the one-pass fallback in both passes.  The wide list needs n < 2^32 / 193 = 22 M particles per device; above that,
-  // and for the warp-per-cell search (its staged lists are kListMax long), the list is kListMax deep.
+  // the one-pass fallback in both passes.  The wide list needs n < 2^32 / 193 = 22 M particles per device; above that
+  // the list is kListMax deep.
   uint32_t cap = (uint32_t)ctx->list_cap;
-  if (cap == kListWide && (ctx->search_mode == 1 || (uint64_t)stride * (kListWide + 1) >= (1ull << 32))) cap = kListMax;
+  if (cap == kListWide && (uint64_t)stride * (kListWide + 1) >= (1ull << 32)) cap = kListMax;
   if ((uint64_t)stride * (cap + 1) >= (1ull << 32))
     return fail(ctx, PBF_ERR_INVALID, "n", "too many particles on one device (neighbour-list indexing)");
-  PBF_CUDA(ctx, ctx->nl.reserve((size_t)stride * (cap + 1)));  // + the dump row of cell_search.cu
+  PBF_CUDA(ctx, ctx->nl.reserve((size_t)stride * (cap + 1)));
   PBF_CUDA(ctx, ctx->nl_count.reserve(n));
   ctx->nl_stride = stride;
   ctx->nl_cap = cap;
-  if (cap == 64)
-    return launch_lambda_cap<64>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
   if (cap == kListWide)
     return launch_lambda_cap<kListWide>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
   return launch_lambda_cap<kListMax>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
@@ -337,9 +289,7 @@ int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint3
 int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
                       const float4 *pstar_in, float4 *pstar_out, const uint32_t *role, uint32_t want) {
   if (count == 0) return PBF_OK;
-  if (ctx->nl_cap == 64)  // the capacity the lambda pass of this iteration wrote the list with
-    return launch_delta_cap<64>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
-  if (ctx->nl_cap == kListWide)
+  if (ctx->nl_cap == kListWide)  // the capacity the lambda pass of this iteration wrote the list with
     return launch_delta_cap<kListWide>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
   return launch_delta_cap<kListMax>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
 }

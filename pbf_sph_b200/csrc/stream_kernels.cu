@@ -192,7 +192,6 @@ int launch_reorder(pbf_ctx *ctx, const uint32_t *perm, const float4 *pos_in, con
 }
 
 int launch_cell_table(pbf_ctx *ctx, const uint32_t *keys_sorted, uint32_t *table) {
-  ctx->plan_valid = false;  // the per-step search plan (cell_search.cu) is derived from this table
   if (ctx->sc.G == 0) return PBF_OK;
   PhaseScope ps(ctx, PBF_PH_CELL_TABLE);
   cell_table_kernel<<<div_up(ctx->sc.G, kBlock), kBlock, 0, ctx->stream>>>(keys_sorted, ctx->sc.n, ctx->sc.G, table);

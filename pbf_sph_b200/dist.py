@@ -101,6 +101,13 @@ class LocalGroup:
         s = self.solvers[0]
         s._ck(s._L.pbf_dist_step(s._ctx, C.byref(params)))
 
+    def advance(self, params: Params, xs: np.ndarray) -> None:
+        """sph::Solver::advance over the group: `xs` in place, back in the global Z order (pbf_dist_advance_host)."""
+        assert xs.dtype == PARTICLE and xs.flags.c_contiguous
+        s = self.solvers[0]
+        nv = C.c_uint64(0)
+        s._ck(s._L.pbf_dist_advance_host(s._ctx, C.byref(params), xs.ctypes.data, len(xs), C.byref(nv)))
+
     def sync(self) -> None:
         for s in self.solvers:
             s.sync()

@@ -54,6 +54,10 @@ class Solver:
     def set_flags(self, flags: int) -> None:
         self._ck(self._L.pbf_set_flags(self._ctx, flags))
 
+    def set_list_capacity(self, hits: int) -> None:
+        """Parity tests only: depth of the per-iteration neighbour list (192 by default, 96 the other compiled depth)."""
+        self._ck(self._L.pbf_debug_set_list_capacity(self._ctx, hits))
+
     def set_stream(self, cuda_stream: int) -> None:
         self._ck(self._L.pbf_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 

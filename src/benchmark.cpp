@@ -3,7 +3,9 @@
 // binary keep working with `-i cuda`.  The reference's own driver cannot be built offline (glm, OpenCL ICD and
 // polyscope are fetched by CMake); INTEGRATION.md shows the `case Impl::CUDA` a maintainer adds there instead.
 //
-//   benchmark [-i cuda] [-d N] [-n iter] [-w warmup] [-o dir] [-l] [-v] [--fp64]          reference flags
+//   benchmark [-i cuda] [-d N[,N...]] [-n iter] [-w warmup] [-o dir] [-l] [-v] [--fp64]   reference flags (-d is a LIST of
+//                                                          devices like the reference's, args.cpp:20-23; may be repeated)
+//             [--gpus N]              shorthand for -d 0,1,...,N-1: the step runs slab-decomposed over N devices
 //             [--scene 2cubes|dam] [--particles N] [--solver-iters I] [--surface on|off]     extensions
 //             [--resident]            keep the particles on the device between frames (pbf_upload/step/download)
 //             [--no-pin]              do not page-lock the particle vector (advance() then copies through pageable memory)
@@ -35,7 +37,8 @@ using Params = sph::SphParams<size_t, float, pbf::vec>;
 using Result = sph::Result<size_t, float, pbf::vec>;
 
 struct Options {
-  std::string impl = "cuda", output = "./out_{impl}_{type}_{iter}", scene = "2cubes", device = "0", saveState, loadState;
+  std::string impl = "cuda", output = "./out_{impl}_{type}_{iter}", scene = "2cubes", saveState, loadState;
+  std::vector<int> devices;  // -d/--devices (a list, args.cpp:20-23); empty = device 0
   size_t iterations = 200, warmup = 200, particles = 20000, solverIter = 6;
   bool list = false, verbose = false, fp64 = false, surface = true, resident = false, fountain = false, help = false, pin = true;
 };
@@ -46,7 +49,9 @@ static void usage() {
                "      -i[impl], --impl=[impl] Which implementation to use. One of: cuda  Default: cuda\n"
                "      -l, --list              List devices available for [impl] and exit\n"
                "      -v, --verbose           Show details such as device tree for [impl]\n"
-               "      -d[dev], --devices=[dev] CUDA device ordinal. Default: 0\n"
+               "      -d[dev...], --devices=[dev...] CUDA device ordinals (comma-separated and/or repeated); more than one =\n"
+               "                              Z-curve slab decomposition over those GPUs. Default: 0\n"
+               "      --gpus=[N]              Same as -d 0,1,...,N-1\n"
                "      -n[iter], --iter=[iter] How many iterations to run the simulation for. Default: 200\n"
                "      -w[warmup], --warmup=[warmup] Iterations to skip for warmup before timing starts. Default: 200\n"
                "      --fp64                  Use FP64 (not supported by the CUDA backend)\n"
@@ -91,7 +96,16 @@ static Options parse(int argc, char **argv) {
     else if (a == "--no-pin") o.pin = false;
     else if (a == "--fountain") o.fountain = true;
     else if (take(argc, argv, i, "i", "impl", v)) o.impl = v;
-    else if (take(argc, argv, i, "d", "devices", v)) o.device = v;
+    else if (take(argc, argv, i, "d", "devices", v)) {
+      for (size_t b = 0; b <= v.size();) {  // "0,1,2" and repeated -d both extend the list
+        const size_t e = std::min(v.find(',', b), v.size());
+        if (e > b) o.devices.push_back(std::stoi(v.substr(b, e - b)));
+        b = e + 1;
+      }
+    } else if (take(argc, argv, i, nullptr, "gpus", v)) {
+      o.devices.clear();
+      for (int d = 0; d < std::stoi(v); ++d) o.devices.push_back(d);
+    }
     else if (take(argc, argv, i, "n", "iter", v)) o.iterations = std::stoull(v);
     else if (take(argc, argv, i, "w", "warmup", v)) o.warmup = std::stoull(v);
     else if (take(argc, argv, i, "o", "output", v)) o.output = v;
@@ -180,7 +194,14 @@ int main(int argc, char *argv[]) {
   }
   std::string output = replaceAll(replaceAll(replaceAll(o.output, "{iter}", std::to_string(o.iterations)), "{type}", "fp32"), "{impl}", o.impl);
   try {
-    sph::cuda_impl::Solver<size_t, float, pbf::vec> solver(0.1f, std::stoi(o.device), o.pin);  // h = 0.1, benchmark.cpp:160-163
+    if (o.devices.empty()) o.devices.push_back(0);
+    if (o.devices.size() > 1 && (o.resident || o.fountain))
+      throw std::runtime_error("--resident and --fountain drive a single device");
+    if (o.devices.size() > 1 && o.surface) {
+      std::cout << "surface extraction is a single-device feature: disabled for the " << o.devices.size() << "-device run" << std::endl;
+      o.surface = false;
+    }
+    sph::cuda_impl::Solver<size_t, float, pbf::vec> solver(0.1f, o.devices, o.pin);  // h = 0.1, benchmark.cpp:160-163
     const float scaling = 500;  // benchmark.cpp:25
     auto [mc, param, particles] = o.scene == "dam"
         ? sph::damBreak<size_t, float, pbf::vec>(static_cast<size_t>(std::cbrt(double(o.particles)) + 0.5), o.solverIter, scaling)

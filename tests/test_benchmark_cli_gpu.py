@@ -118,3 +118,24 @@ def test_pinned_caller_memory_gives_the_same_particles(gpu, tmp_path):
         assert out.returncode == 0, out.stderr
         outs.append((tmp_path / (tag + "_3") / "cloud.ply").read_bytes())
     assert outs[0] == outs[1]
+
+
+def test_device_list_runs_the_slab_path_and_matches_one_device(gpu, tmp_path):
+    """-d is a device LIST like the reference's (args.cpp:20-23); more than one entry = the Z-curve slab decomposition
+    behind the same sph::Solver::advance.  On this 1-GPU box the four ranks share device 0: cloud.ply must be
+    byte-identical to the single-device run's."""
+    common = ["--scene=dam", "--particles=64000", "--solver-iters=4", "--surface=off", "-n", "4", "-w", "3"]
+    one = run(*common, "-d", "0", "-o", str(tmp_path / "one_{iter}"))
+    four = run(*common, "-d", "0,0", "-d", "0", "-d0", "-o", str(tmp_path / "four_{iter}"))
+    assert one.returncode == 0 and four.returncode == 0, one.stderr + four.stderr
+    assert "Final Particle count : 64000" in four.stdout
+    a, b = (tmp_path / "one_4" / "cloud.ply").read_bytes(), (tmp_path / "four_4" / "cloud.ply").read_bytes()
+    assert len(a) > 64000 * 32 and a == b
+    # the stock scene with its moving wall, surface requested: the slab run says it drops the surface and still matches
+    stock = ["--particles=20000", "--solver-iters=4", "-n", "3", "-w", "2"]
+    one = run(*stock, "--surface=off", "-o", str(tmp_path / "s1_{iter}"))
+    two = run(*stock, "-d", "0,0", "-o", str(tmp_path / "s2_{iter}"))
+    assert one.returncode == 0 and two.returncode == 0, one.stderr + two.stderr
+    assert (tmp_path / "s1_3" / "cloud.ply").read_bytes() == (tmp_path / "s2_3" / "cloud.ply").read_bytes()
+    assert run("--gpus=2", "--resident", "-n1", "-w0", "-o", "").returncode != 0
+    assert run("-d", "0,99", "-n1", "-w0", "-o", "").returncode != 0  # no such device

@@ -100,3 +100,43 @@ def test_slab_path_rejects_surface_and_single_device_calls(gpu):
         p.surface_enabled = 1
         with pytest.raises(capi.PbfError):
             g.step(p)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_group_advance_equals_single_device_advance(gpu, world):
+    """pbf_dist_advance_host (what sph::cuda_impl::Solver(h, {devices...})::advance calls): the caller's array goes in,
+    comes back in the global Z order — byte for byte what pbf_advance_host returns on one device, frame after frame
+    (the array returned by one call is the next call's input, as in the reference's drivers, benchmark.cpp:22-58)."""
+    p, xs = scenes.two_cubes(20000, 4)
+    one, many = xs.copy(), xs.copy()
+    with Solver(H, 0) as s, LocalGroup(H, [0] * world) as g:
+        for f in range(6):
+            pf = scenes.apply_motion(p, f)
+            s.advance(pf, one)
+            g.advance(pf, many)
+            assert many.tobytes() == one.tobytes(), f"frame {f}"
+        # a different array size mid-run (the caller dropped particles): blocks are re-cut, still identical
+        one, many = one[:9000].copy(), many[:9000].copy()
+        s.advance(p, one)
+        g.advance(p, many)
+        assert many.tobytes() == one.tobytes()
+    xs["type"][7] = 1
+    with LocalGroup(H, [0] * world) as g, pytest.raises(capi.PbfError):
+        g.advance(p, xs)
+
+
+def test_group_on_distinct_devices(gpu):
+    """One process driving two different GPUs (pbf_dist_init_local with distinct ordinals): per-device kernel attributes
+    (the tiled diffusion opts in to > 48 KB of shared memory per DEVICE) and peer copies."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    p, xs = scenes.two_cubes(20000, 4)
+    ref = run_single(p, xs.copy(), 4, True)
+    out = []
+    with LocalGroup(H, [0, 1]) as g:
+        g.upload(xs)
+        for f in range(4):
+            g.step(scenes.apply_motion(p, f))
+        out = g.download()
+    assert out.tobytes() == ref[-1].tobytes()
