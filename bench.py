@@ -14,6 +14,11 @@
   region) against MEASURED_PEAKS.json; `cpu_baseline` = the reference OpenMP backend (oracle/_ref, built from the
   unmodified sources) on this box's host cores on a bounded sample.
 * --impl reference times that same reference CPU implementation as the driver's comparison arm.
+* `secondary` = BASELINE.json's other named configurations measured in the same run with few steps:
+  N = 1: dam-1m-mc (configs[3]), dam-8m on one GPU (configs[2]'s baseline), dam-8m with 8 iterations (configs[4]'s
+  first point); N > 1: dam-8m split N ways (configs[2], strong scaling) and dam-weak-8m (configs[4], ~8 M per GPU,
+  8 iterations), each with its own single-GPU figure measured by rank 0 in the same job.
+* N > 1: `parity` = 6 moving-wall frames of the stock scene on the N-rank NCCL group against one device, bit for bit.
 """
 from __future__ import annotations
 
@@ -212,7 +217,8 @@ def reference_cpu(params, xs, steps, warmup, settle_steps=100, budget_s=150.0):
     per_particle = t_probe / len(probe)
     settle = settle_steps
     n_budget = budget_s / max(1, steps + warmup + settle) / per_particle
-    if n_budget >= len(xs):
+    same = n_budget >= len(xs)
+    if same:
         p, a, sample = params, xs.copy(), f"the full workload ({len(xs)} particles)"
     else:
         side = max(24, int(n_budget ** (1 / 3)))
@@ -226,8 +232,11 @@ def reference_cpu(params, xs, steps, warmup, settle_steps=100, budget_s=150.0):
         advance(p, a)
     dt = time.perf_counter() - t0
     pis = len(a) * int(p.iteration) * steps / dt
+    note = ("; each call constructs the reference's solver and copies the particle vector in and out (a few % at 1 M); the "
+            "reference settles its own fluid with its in-place (Gauss-Seidel, racy) delta pass, the GPU arm with the Jacobi form, "
+            "so the two arms time statistically equal but not identical fluid states")
     return pis, dt / steps * 1e3, cores, kind, (f"{sample}, settled {settle} steps by the reference itself, then {warmup} warm-up "
-                                                f"+ {steps} timed steps; {variant}; {cores} threads")
+                                                f"+ {steps} timed steps; {variant}; {cores} threads" + note), same, len(a)
 
 
 def run_reference(args):
@@ -235,11 +244,13 @@ def run_reference(args):
     if rank != 0:
         return
     name, desc, p, xs = workload(args.workload, max(1, args.gpus))
-    pis, ms, cores, kind, sample = reference_cpu(p, xs, args.steps, args.warmup, args.settle)
+    pis, ms, cores, kind, sample, same, n_timed = reference_cpu(p, xs, args.steps, args.warmup, args.settle, budget_s=args.ref_budget)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": pis, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": desc, "name": name},
+        # false = the CPU arm timed a smaller block of the same scene family than the GPU arm's workload (bounded sample)
+        "same_config": bool(same), "particles_timed": int(n_timed), "particles_workload": int(len(xs)),
         "cpu_baseline": {"value": pis, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": pis, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -279,9 +290,66 @@ def roofline_of(prof, n, iters, steps):
 
 
 # ------------------------------------------------------------------------------------------------ our arm, 1 GPU
+def time_resident(torch, s, stream, p, steps):
+    """K resident steps between two CUDA events on the solver's stream -> (ms total, launches)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = s.launch_count()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        s.step(p)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), s.launch_count() - l0
+
+
+def profiled_pass(torch, s, stream, p, steps, flags, families=None):
+    """The same K steps with the library's CUDA events around the given kernel families (None = all)."""
+    from pbf_sph_b200 import FLAG_PROFILE
+    s.set_flags(FLAG_PROFILE | flags)
+    s.profile_mask(families)
+    s.profile_reset()
+    ms, _ = time_resident(torch, s, stream, p, steps)
+    prof = s.profile()
+    s.set_flags(flags)
+    s.profile_mask(None)
+    return ms, prof
+
+
+def secondary_single(torch, s, stream, args, which):
+    """BASELINE.json's other configurations on ONE GPU, few steps each: settle, warm up, time K resident steps, then one
+    profiled pass for the per-family milliseconds."""
+    out = []
+    k = max(3, args.secondary_steps)
+    for name, iters_list in which:
+        wname, desc, p, xs = workload(name, 1)
+        s.upload(xs)
+        n = len(xs)
+        del xs
+        for _ in range(args.settle):
+            s.step(p)
+        for iters in iters_list:
+            p.iteration = iters
+            for _ in range(3):
+                s.step(p)
+            ms, launches = time_resident(torch, s, stream, p, k)
+            _, prof = profiled_pass(torch, s, stream, p, k, args.flags)
+            entry = {"name": wname if iters == iters_list[0] else f"{wname}-{iters}it", "workload": desc if iters == iters_list[0]
+                     else desc.replace(f"{iters_list[0]} solver iterations", f"{iters} solver iterations"),
+                     "n_gpus": 1, "particles": n, "solver_iterations": iters, "steps": k, "settle_steps": args.settle,
+                     "ms_per_step": ms / k, "value": n * iters * k / (ms * 1e-3), "unit": UNIT,
+                     "us_per_particle_step": ms / k * 1e3 / n, "gpu_launches": launches,
+                     "ms_per_step_by_family": {f: round(v / k, 4) for f, v in prof["ms"].items() if v > 0}}
+            if p.surface_enabled:
+                s.sync()
+                entry["triangles"] = int(s.grid().n_triangles)
+            out.append(entry)
+    return out
+
+
 def run_single(args):
     import torch
-    from pbf_sph_b200 import FLAG_PROFILE, PARTICLE, Solver, capi, scenes
+    from pbf_sph_b200 import FLAG_DEBUG_COUNTS, PARTICLE, Solver, capi, scenes
     name, desc, p, xs = workload(args.workload, 1)
     n, iters = len(xs), int(p.iteration)
     dev = int(os.environ.get("LOCAL_RANK", "0"))
@@ -297,39 +365,36 @@ def run_single(args):
     for _ in range(args.warmup):
         s.step(p)
     s.sync()
-    s.profile_reset()
-    l0 = s.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     with ClockSampler(dev, period=0.05) as clk:
-        e0.record(stream)
-        for _ in range(args.steps):
-            s.step(p)
-        e1.record(stream)
-        torch.cuda.synchronize()
-    ms_total = e0.elapsed_time(e1)
-    launches = s.launch_count() - l0
+        ms_total, launches = time_resident(torch, s, stream, p, args.steps)
     value = n * iters * args.steps / (ms_total * 1e-3)
-    # the same K steps again with the library's per-family CUDA events on (PBF_FLAG_PROFILE: ~30 event records per
-    # step, ~2 % of the step, which is why `value` above is timed without them): the roofline's launch durations
-    s.set_flags(FLAG_PROFILE | args.flags)
-    s.profile_reset()
-    torch.cuda.synchronize()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    for _ in range(args.steps):
-        s.step(p)
-    e3.record(stream)
-    torch.cuda.synchronize()
-    ms_profiled = e2.elapsed_time(e3)
-    prof = s.profile()
-    s.set_flags(args.flags)
-
+    # Kernel durations: (a) every family timed (~30 event records per step — they stretch a 1.8 ms step by up to a fifth,
+    # which is why `value` is timed without them): the per-family breakdown; (b) the two solver families alone (16 records
+    # per step): the launch duration the roofline uses.
+    ms_all, prof = profiled_pass(torch, s, stream, p, args.steps, args.flags)
+    ms_dom, prof_dom = profiled_pass(torch, s, stream, p, args.steps, args.flags, ["lambda", "delta"])
+    for f in ("lambda", "delta"):
+        prof["ms"][f], prof["launches"][f] = prof_dom["ms"][f], prof_dom["launches"][f]
     roofline = roofline_of(prof, n, iters, args.steps)
-    roofline["region"] = (f"{args.steps} further steps with per-family CUDA events recorded by the library on its stream "
-                          f"({ms_profiled / args.steps:.4f} ms/step with events, {ms_total / args.steps:.4f} without)")
-    # the ceiling that does apply to the neighbour passes: warp-instruction issue slots (SMs x 4 schedulers x SM clock);
-    # instructions per launch from the committed ncu capture, duration live
+    roofline["region"] = (f"{args.steps} further steps with CUDA events recorded by the library on its stream around the lambda / delta "
+                          f"launches only ({ms_dom / args.steps:.4f} ms/step; {ms_total / args.steps:.4f} without any events, "
+                          f"{ms_all / args.steps:.4f} with every family timed — the other families' figures come from that pass)")
+    # what the neighbour passes are really limited by: pair tests / evaluations per second and issue slots
+    s.set_flags(FLAG_DEBUG_COUNTS | args.flags)
+    s.step(p)
+    s.sync()
+    cand, hits = s.tap(capi.TAP_CAND_COUNT).astype(np.int64), s.tap(capi.TAP_NBR_COUNT).astype(np.int64)
+    s.set_flags(args.flags)
+    lam_ms = prof["ms"]["lambda"] / max(1, prof["launches"]["lambda"])
+    del_ms = prof["ms"]["delta"] / max(1, prof["launches"]["delta"])
+    roofline["limiter"] = "latency / issue (not HBM): see `pairs` and `issue`"
+    roofline["pairs"] = {
+        "candidates_per_particle": float(cand.mean()), "neighbours_per_particle": float(hits.mean()),
+        "pair_tests_per_s": float(cand.sum() / (lam_ms * 1e-3)),
+        "pair_evaluations_per_s": float(2 * hits.sum() / ((lam_ms + del_ms) * 1e-3)),
+        "note": "tests = 27-cell candidates the lambda pass's search examines per launch / its launch duration (the search "
+                "shares the launch with the sums over the hits); evaluations = kernel-function evaluations of the lambda and "
+                "delta passes (one per in-radius pair each) / their combined duration"}
     tf = ROOT / "profiles" / "ncu_traffic.json"
     if tf.exists():
         t = json.loads(tf.read_text())
@@ -343,6 +408,9 @@ def run_single(args):
                                  "warp_inst_per_launch": inst,
                                  "source": "smsp__inst_executed.sum of one launch (" + t.get("source", "ncu") + "); peak = "
                                            f"{sms} SMs x 4 schedulers x {clocks['sm_mhz']:.0f} MHz"}
+        if t.get("particles") == n and t.get("fma_pipe_pct", {}).get(roofline["kernel"]) is not None:
+            roofline["fp32_pipe_utilisation_pct"] = {"value": t["fma_pipe_pct"][roofline["kernel"]],
+                                                      "source": "sm__inst_executed_pipe_fma (ncu capture, " + t.get("source", "") + ")"}
 
     # end to end through the drop-in call, pinned host buffers
     snap = s.download()
@@ -391,6 +459,14 @@ def run_single(args):
             t0 = time.perf_counter(); oracle.step(scenes.H, p, a); t1 = time.perf_counter() - t0
             cpu = {"value": n * iters / t1, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "1 step of the full workload; oracle Jacobi restatement (oracle/_ref absent)"}
+    del snap
+    secondary = None
+    if not args.no_secondary and args.workload in ("auto", "dam-1m"):
+        # BASELINE.json configs[3] (surface every step), configs[2] on one GPU, and configs[4]'s first point (8 M, 8 iterations)
+        secondary = secondary_single(torch, s, stream, args, [("dam-1m-mc", [4]), ("dam-8m", [4, 8])])
+        base = ms_total / args.steps * 1e3 / n
+        for e in secondary:
+            e["us_per_particle_step_vs_dam_1m"] = e["us_per_particle_step"] / base if e["solver_iterations"] == iters else None
     s.close()
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -402,7 +478,7 @@ def run_single(args):
                          "the 126 MB L2"},
         "particle_steps_per_sec": n * args.steps / (ms_total * 1e-3),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-        "clocks": clk.summary(),
+        "clocks": clk.summary(), "secondary": secondary,
     }
     print(json.dumps(out))
 
@@ -431,6 +507,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE's other configurations (`secondary`)")
+    ap.add_argument("--secondary-steps", type=int, default=10)
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="--impl reference: seconds of CPU time for settle + warm-up + timed steps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="extra PBF_FLAG_* bits (1 strict fp, 8 global-memory neighbours)")
     args = ap.parse_args()

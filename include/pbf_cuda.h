@@ -239,6 +239,10 @@ int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes);
 int pbf_debug_set_list_capacity(pbf_ctx *ctx, uint32_t hits);
 int pbf_profile_reset(pbf_ctx *ctx);
 int pbf_profile_read(pbf_ctx *ctx, pbf_profile *out);
+/* Families timed under PBF_FLAG_PROFILE: bit f = PBF_PH_f (default: all).  Every timed launch costs two event records
+ * on the stream (~30 per step with all families on, which stretches a 1.8 ms step by a fifth); bench.py times the
+ * dominant family alone (8 records per step) for the roofline's launch duration. */
+int pbf_profile_set_mask(pbf_ctx *ctx, uint32_t family_mask);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t pbf_launch_count(const pbf_ctx *ctx);
 

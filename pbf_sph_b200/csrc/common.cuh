@@ -55,7 +55,8 @@ struct StepConst {
   float min_extent[3];      // ompsph.hpp:133
   uint32_t extent[3];       // ompsph.hpp:135
   uint32_t G;               // sph.hpp:240
-  uint32_t n;               // particles
+  uint32_t n;               // particles (slab path: an upper bound that sizes the grid when n_dyn is set)
+  const uint32_t *n_dyn;    // slab path: the count lives in device memory (the host never reads it back); else nullptr
   float P6, SP, P6dq;       // sph.hpp:251-253, ompsph.hpp:211-213
   float r2_max;             // largest float r2 with sqrtf(r2) <= h  (same neighbour set as "r <= h")
   float r2_min;             // smallest float r2 with sqrtf(r2) >= EPSILON
@@ -131,6 +132,33 @@ __device__ __forceinline__ void predict(const StepConst &c, const float4 pos_mas
 // 128-bit read-only loads/stores
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
+// number of particles a kernel covers: by value, or from device memory on the slab path
+__device__ __forceinline__ uint32_t count_of(const StepConst &c) { return c.n_dyn ? __ldg(c.n_dyn) : c.n; }
+
+// Which particles one launch of a solver pass processes.  Thread t takes particle
+//     first + t          for t < count           (a contiguous range of the sorted array), then
+//     idx[t - count]     for t - count < n_idx   (a compacted index list: ring-1 ghosts, boundary / interior particles)
+// On the slab path count / n_idx are read from device memory (count_dev / n_idx_dev) and `bound` sizes the grid.
+struct Sel {
+  uint32_t first = 0, count = 0, n_idx = 0;
+  const uint32_t *count_dev = nullptr, *idx = nullptr, *n_idx_dev = nullptr;
+  uint32_t bound = 0;  // host-side upper bound of count + n_idx
+};
+__device__ __forceinline__ bool sel_particle(const Sel &s, uint32_t t, uint32_t &a) {
+  const uint32_t count = s.count_dev ? __ldg(s.count_dev) : s.count;
+  if (t < count) { a = s.first + t; return true; }
+  if (!s.idx) return false;
+  const uint32_t k = t - count;
+  if (k >= (s.n_idx_dev ? __ldg(s.n_idx_dev) : s.n_idx)) return false;
+  a = __ldg(s.idx + k);
+  return true;
+}
+inline Sel sel_range(uint32_t first, uint32_t count) {
+  Sel s;
+  s.first = first; s.count = count; s.bound = count;
+  return s;
+}
+
 // ---- device buffer with geometric growth ------------------------------------------------------------
 template <typename T> struct DevBuf {
   T *p = nullptr;
@@ -186,6 +214,7 @@ struct pbf_ctx {
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;
+  const uint32_t *diffuse_local_range = nullptr;  // slab path: {first, count} of the local array (device memory), see diffuse_tiled.cu
   int diffuse_blocks_per_sm = 0;  // diffuse_tiled.cu: resident blocks per SM on THIS context's device (0 = not set up yet)
 
   uint64_t n = 0;  // resident particles
@@ -243,6 +272,7 @@ struct pbf_ctx {
   int ev_used = 0;
   bool ev_created = false;
   pbf_profile prof{};
+  uint32_t prof_mask = 0xFFFFFFFFu;  // families timed under PBF_FLAG_PROFILE (bit = PBF_PH_*), pbf_profile_set_mask
 };
 
 namespace pbf {
@@ -281,11 +311,15 @@ int launch_pack_aos(pbf_ctx *ctx, pbf_particle *aos, uint64_t n, const float4 *p
 int launch_predict_key(pbf_ctx *ctx, const float4 *pos, const float4 *vel, uint32_t *keys);
 // Stable LSD radix sort of (key, index) pairs over all 30 key bits; on return ctx->keys_sorted / ctx->perm are set.
 // vals_in == nullptr sorts (key, 0..n-1); otherwise the given values travel with the keys (multi-GPU merge, dist.cu).
-int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n, const uint32_t *vals_in = nullptr);
+// n_dev != nullptr: the pair count lives in device memory and n is its upper bound (slab path).
+int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n, const uint32_t *vals_in = nullptr,
+                     const uint32_t *n_dev = nullptr);
 int launch_reorder(pbf_ctx *ctx, const uint32_t *perm, const float4 *pos_in, const float4 *vel_in, const float4 *col_in,
                    const unsigned long long *ids_in, float4 *pos_out, float4 *vel_out, float4 *col_out,
                    unsigned long long *ids_out, float4 *pstar_out);
-int launch_cell_table(pbf_ctx *ctx, const uint32_t *keys_sorted, uint32_t *table);
+// table[z] = first index in [0, n) whose key >= z; with range_dev = {first, count} in device memory the search runs over
+// keys_sorted[first .. first + count) and the table holds absolute indices (slab path: the local array starts at `first`).
+int launch_cell_table(pbf_ctx *ctx, const uint32_t *keys_sorted, uint32_t *table, const uint32_t *range_dev = nullptr);
 int launch_neighbour_counts(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *pstar,
                             uint32_t *cand, uint32_t *nbr);
 int launch_diffuse(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *col_in, float4 *col_out);
@@ -302,21 +336,19 @@ int launch_delta_global(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint
 // neighbour-list kernels (neighbour_list.cu): the production lambda/delta passes
 constexpr uint32_t kListMax = 96;    // list depth above 22 M particles per device (32-bit list indexing), and the A/B depth of the tests
 constexpr uint32_t kListWide = 192;  // production depth; a particle with more hits takes the one-pass path in both passes
-int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                       const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
-                       const uint32_t *role = nullptr, uint32_t want = 0);
-// role != nullptr: particle a is processed only when role[a] & want (multi-GPU: ring-1 / boundary / interior, dist.cu)
-int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                      const float4 *pstar_in, float4 *pstar_out, const uint32_t *role = nullptr, uint32_t want = 0);
-// The production lambda / delta pass over the sorted range [first, first + count) (neighbour-list kernels, or the
-// one-pass global kernels under PBF_FLAG_GLOBAL_NEIGHBOURS).
-int solver_lambda(pbf_ctx *ctx, uint32_t first, uint32_t count, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
-                  const uint32_t *role = nullptr, uint32_t want = 0);
-int solver_delta(pbf_ctx *ctx, uint32_t first, uint32_t count, const float4 *pstar_in, float4 *pstar_out,
-                 const uint32_t *role = nullptr, uint32_t want = 0);
-// shared-memory tiled colour diffusion (diffuse_tiled.cu)
+int launch_lambda_list(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,
+                       const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out);
+int launch_delta_list(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,
+                      const float4 *pstar_in, float4 *pstar_out);
+// The production lambda / delta pass over the selected particles (neighbour-list kernels, or the one-pass global kernels
+// under PBF_FLAG_GLOBAL_NEIGHBOURS, which take contiguous ranges only).  list_particles = size of the sorted array the
+// neighbour list spans (its row stride); 0 = ctx->sc.n.
+int solver_lambda(pbf_ctx *ctx, const Sel &sel, const float4 *pstar_in, float4 *pstar_out, float *rho_out);
+int solver_delta(pbf_ctx *ctx, const Sel &sel, const float4 *pstar_in, float4 *pstar_out);
+// shared-memory tiled colour diffusion (diffuse_tiled.cu).  own_range_dev = {first, count} in device memory: only cell
+// blocks holding particles of that index range are processed (slab path: ghosts get their colours from their owners).
 int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *col_in,
-                         float4 *col_out);
+                         float4 *col_out, const uint32_t *own_range_dev = nullptr);
 int launch_finalise(pbf_ctx *ctx, const float4 *pstar, float4 *pos, float4 *vel);
 // opt-in extension after finalise (xsph.cu): XSPH viscosity / vorticity confinement per ctx->flags
 int launch_xsph_vorticity(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *pstar, float4 *vel,

@@ -104,7 +104,7 @@ static const char *const kPhaseNames[PBF_PH_COUNT] = {
 
 PhaseScope::PhaseScope(pbf_ctx *c, int ph) : ctx(c), phase(ph), slot(-1) {
   nvtxRangePushA(kPhaseNames[ph]);
-  if (!(ctx->flags & PBF_FLAG_PROFILE)) return;
+  if (!(ctx->flags & PBF_FLAG_PROFILE) || !((ctx->prof_mask >> ph) & 1u)) return;
   if (!ctx->ev_created) {
     for (int i = 0; i < pbf_ctx::kMaxEv; ++i) cudaEventCreate(&ctx->ev[i]);
     ctx->ev_created = true;
@@ -134,21 +134,23 @@ static void profile_collect(pbf_ctx *ctx) {
 }
 
 // ---- the step ------------------------------------------------------------------------------------------------------
-int solver_lambda(pbf_ctx *ctx, uint32_t first, uint32_t count, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
-                  const uint32_t *role, uint32_t want) {
+int solver_lambda(pbf_ctx *ctx, const Sel &sel, const float4 *pstar_in, float4 *pstar_out, float *rho_out) {
   PhaseScope ps(ctx, PBF_PH_LAMBDA);
   const float4 *pos_mass = ctx->pos[ctx->cur].p;
-  if (ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS)
-    return launch_lambda_global(ctx, first, count, ctx->keys_sorted, ctx->table.p, pos_mass, pstar_in, pstar_out, rho_out);
-  return launch_lambda_list(ctx, first, count, ctx->keys_sorted, ctx->table.p, pos_mass, pstar_in, pstar_out, rho_out, role, want);
+  if (ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS) {
+    if (sel.idx || sel.count_dev) return fail(ctx, PBF_ERR_STATE, "PBF_FLAG_GLOBAL_NEIGHBOURS", "contiguous host-sized ranges only (not on the slab path)");
+    return launch_lambda_global(ctx, sel.first, sel.count, ctx->keys_sorted, ctx->table.p, pos_mass, pstar_in, pstar_out, rho_out);
+  }
+  return launch_lambda_list(ctx, sel, ctx->keys_sorted, ctx->table.p, pos_mass, pstar_in, pstar_out, rho_out);
 }
 
-int solver_delta(pbf_ctx *ctx, uint32_t first, uint32_t count, const float4 *pstar_in, float4 *pstar_out, const uint32_t *role,
-                 uint32_t want) {
+int solver_delta(pbf_ctx *ctx, const Sel &sel, const float4 *pstar_in, float4 *pstar_out) {
   PhaseScope ps(ctx, PBF_PH_DELTA);
-  if (ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS)
-    return launch_delta_global(ctx, first, count, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out);
-  return launch_delta_list(ctx, first, count, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out, role, want);
+  if (ctx->flags & PBF_FLAG_GLOBAL_NEIGHBOURS) {
+    if (sel.idx || sel.count_dev) return fail(ctx, PBF_ERR_STATE, "PBF_FLAG_GLOBAL_NEIGHBOURS", "contiguous host-sized ranges only (not on the slab path)");
+    return launch_delta_global(ctx, sel.first, sel.count, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out);
+  }
+  return launch_delta_list(ctx, sel, ctx->keys_sorted, ctx->table.p, pstar_in, pstar_out);
 }
 
 static int validate(pbf_ctx *ctx, const pbf_params *p) {
@@ -231,12 +233,12 @@ static int step_device(pbf_ctx *ctx, const pbf_params &p) {
   }
   ctx->cur_col ^= 1;
   for (uint64_t it = 0; it < p.iteration; ++it) {
-    PBF_TRY(solver_lambda(ctx, 0, n, ctx->pstar[0].p, ctx->pstar[1].p, it + 1 == p.iteration ? ctx->rho.p : nullptr));
+    PBF_TRY(solver_lambda(ctx, sel_range(0, n), ctx->pstar[0].p, ctx->pstar[1].p, it + 1 == p.iteration ? ctx->rho.p : nullptr));
     if (it == 0 && (ctx->flags & PBF_FLAG_DEBUG_COUNTS) && tiled) {  // PBF_TAP_LIST_HITS
       PBF_CUDA(ctx, ctx->list_hits.reserve(n));
       PBF_CUDA(ctx, cudaMemcpyAsync(ctx->list_hits.p, ctx->nl_count.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    PBF_TRY(solver_delta(ctx, 0, n, ctx->pstar[1].p, ctx->pstar[0].p));
+    PBF_TRY(solver_delta(ctx, sel_range(0, n), ctx->pstar[1].p, ctx->pstar[0].p));
   }
   PBF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   PBF_TRY(launch_finalise(ctx, ctx->pstar[0].p, ctx->pos[ctx->cur].p, ctx->vel[ctx->cur].p));
@@ -598,6 +600,12 @@ int pbf_profile_reset(pbf_ctx *ctx) {
   PBF_ENTER(ctx);
   profile_collect(ctx);
   std::memset(&ctx->prof, 0, sizeof(ctx->prof));
+  return PBF_OK;
+}
+
+int pbf_profile_set_mask(pbf_ctx *ctx, uint32_t family_mask) {
+  PBF_ENTER(ctx);
+  ctx->prof_mask = family_mask;
   return PBF_OK;
 }
 

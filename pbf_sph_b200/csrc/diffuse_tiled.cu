@@ -32,6 +32,7 @@ struct TiledArgs {
   const uint32_t *blk_list;   // occupied blocks
   const uint32_t *blk_count;
   uint32_t *queue;            // work counter of this launch (zeroed once per step)
+  const uint32_t *n_end;      // slab path: {first, count} of the local array in device memory; else nullptr
 };
 
 struct __align__(16) Smem {
@@ -165,8 +166,10 @@ __global__ void __launch_bounds__(kThreads) diffuse_tiled_kernel(StepConst c, Ti
   // Particles with key >= G-1 take the global path: keys >= G are outside the grid (in no cell, but still processed
   // as `a`), and cell G-1 is never visible as a neighbour cell (sph.hpp:203-213), so its own particles cannot be
   // found through the staged halo.
+  // (slab path: g.n_end = one past the last particle of the local array, in device memory; the table holds absolute indices)
+  const uint32_t n_end = g.n_end ? __ldg(g.n_end) + __ldg(g.n_end + 1) : c.n;
   const uint32_t n_in = __ldg(g.table + (c.G - 1u));
-  if (blockIdx.x == 0 && n_in < c.n) diffuse_range_global(c, g, n_in, c.n, c.n);
+  if (blockIdx.x == 0 && n_in < n_end) diffuse_range_global(c, g, n_in, n_end, n_end);
   const uint32_t n_work = __ldg(g.blk_count);
   while (true) {
     __syncthreads();  // the previous block's shared memory is no longer read
@@ -186,17 +189,24 @@ __global__ void __launch_bounds__(kThreads) diffuse_tiled_kernel(StepConst c, Ti
 // occupied-block queue
 __global__ void __launch_bounds__(256) build_block_list_kernel(const uint32_t *__restrict__ table, uint32_t G,
                                                                uint32_t n_blocks, uint32_t *__restrict__ list,
-                                                               uint32_t *__restrict__ ctl) {
+                                                               uint32_t *__restrict__ ctl,
+                                                               const uint32_t *__restrict__ own_range) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   if (b >= n_blocks) return;
   const uint32_t k0 = b << 6;
-  if (__ldg(table + min(k0 + 64u, G - 1u)) > __ldg(table + k0)) list[atomicAdd(ctl, 1u)] = b;
+  const uint32_t s = __ldg(table + k0), e = __ldg(table + min(k0 + 64u, G - 1u));
+  bool take = e > s;
+  if (take && own_range) {  // slab path: a block made of ghosts only is somebody else's work
+    const uint32_t first = __ldg(own_range), last = first + __ldg(own_range + 1);
+    take = s < last && e > first;
+  }
+  if (take) list[atomicAdd(ctl, 1u)] = b;
 }
 
 }  // namespace
 
 int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *col_in,
-                         float4 *col_out) {
+                         float4 *col_out, const uint32_t *own_range_dev) {
   PhaseScope ps(ctx, PBF_PH_DIFFUSE);
   const uint32_t n_blocks = (ctx->sc.G - 1u + 63u) / 64u;  // blocks covering keys [0, G-1)
   PBF_CUDA(ctx, ctx->blk_list.reserve(n_blocks + 1));
@@ -204,7 +214,7 @@ int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32
   PBF_CUDA(ctx, cudaMemsetAsync(ctx->blk_info.p, 0, 2 * sizeof(uint32_t), ctx->stream));
   if (n_blocks) {
     build_block_list_kernel<<<div_up(n_blocks, 256), 256, 0, ctx->stream>>>(table, ctx->sc.G, n_blocks, ctx->blk_list.p,
-                                                                            ctx->blk_info.p);
+                                                                            ctx->blk_info.p, own_range_dev);
     PBF_LAUNCH_CHECK(ctx);
   }
   // Function attributes are per device: the opt-in to > 48 KB of dynamic shared memory and the occupancy are set up once
@@ -216,7 +226,7 @@ int launch_diffuse_tiled(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32
     ctx->diffuse_blocks_per_sm = per_sm < 1 ? 1 : per_sm;
   }
   const int per_sm = ctx->diffuse_blocks_per_sm;
-  TiledArgs g{keys_sorted, table, col_in, col_out, ctx->blk_list.p, ctx->blk_info.p, ctx->blk_info.p + 1};
+  TiledArgs g{keys_sorted, table, col_in, col_out, ctx->blk_list.p, ctx->blk_info.p, ctx->blk_info.p + 1, ctx->diffuse_local_range};
   diffuse_tiled_kernel<<<(unsigned)(ctx->sm_count * per_sm), kThreads, sizeof(Smem), ctx->stream>>>(ctx->sc, g);
   PBF_LAUNCH_CHECK(ctx);
   return PBF_OK;

@@ -113,19 +113,16 @@ __device__ __forceinline__ RowRuns load_row(const uint32_t *__restrict__ table, 
 }
 
 template <bool kStrict, int kCap>
-__global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepConst c, uint32_t first, uint32_t count,
+__global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepConst c, Sel sel,
                                                              const uint32_t *__restrict__ keys,
                                                              const uint32_t *__restrict__ table,
                                                              const float4 *__restrict__ pos_mass,
                                                              const float4 *__restrict__ pstar_in,
                                                              float4 *__restrict__ pstar_out, float *__restrict__ rho_out,
                                                              uint32_t *nl, uint32_t stride, uint32_t inv_stride,
-                                                             uint32_t *__restrict__ n_hits,
-                                                             const uint32_t *__restrict__ role, uint32_t want) {
-  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
-  if (t >= count) return;
-  const uint32_t a = first + t;
-  if (role && !(__ldg(role + a) & want)) return;  // multi-GPU: not this pass's particle (dist.cu roles)
+                                                             uint32_t *__restrict__ n_hits) {
+  uint32_t a;
+  if (!sel_particle(sel, blockIdx.x * kBlock + threadIdx.x, a)) return;
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t key = __ldg(keys + a);
   const float mass = __ldg(&pos_mass[a].w);
@@ -205,18 +202,15 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
 }
 
 template <bool kStrict, int kCap>
-__global__ void __launch_bounds__(kBlock, 8) delta_list_kernel(StepConst c, uint32_t first, uint32_t count,
+__global__ void __launch_bounds__(kBlock, 8) delta_list_kernel(StepConst c, Sel sel,
                                                             const uint32_t *__restrict__ keys,
                                                             const uint32_t *__restrict__ table,
                                                             const float4 *__restrict__ pstar_in,
                                                             float4 *__restrict__ pstar_out,
                                                             const uint32_t *__restrict__ nl, uint32_t stride,
-                                                            const uint32_t *__restrict__ n_hits,
-                                                            const uint32_t *__restrict__ role, uint32_t want) {
-  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
-  if (t >= count) return;
-  const uint32_t a = first + t;
-  if (role && !(__ldg(role + a) & want)) return;
+                                                            const uint32_t *__restrict__ n_hits) {
+  uint32_t a;
+  if (!sel_particle(sel, blockIdx.x * kBlock + threadIdx.x, a)) return;
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t k = __ldg(n_hits + a);
   DeltaAcc<kStrict> acc;
@@ -229,50 +223,47 @@ __global__ void __launch_bounds__(kBlock, 8) delta_list_kernel(StepConst c, uint
   pstar_out[a] = acc.finish(c, pa);
 }
 
-template <int kCap> int launch_lambda_cap(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
-                                          const uint32_t *table, const float4 *pos_mass, const float4 *pstar_in,
-                                          float4 *pstar_out, float *rho_out, uint32_t stride, const uint32_t *role,
-                                          uint32_t want) {
+template <int kCap> int launch_lambda_cap(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,
+                                          const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
+                                          uint32_t stride) {
   uint32_t *nl4 = ctx->nl.p;
+  const uint32_t inv_stride = (uint32_t)(((1ull << 32) + stride - 1) / stride);
   if (ctx->flags & PBF_FLAG_STRICT_FP)
-    lambda_list_kernel<true, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride,
-        (uint32_t)(((1ull << 32) + stride - 1) / stride), ctx->nl_count.p, role, want);
+    lambda_list_kernel<true, kCap><<<div_up(sel.bound, kBlock), kBlock, 0, ctx->stream>>>(
+        ctx->sc, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, inv_stride, ctx->nl_count.p);
   else
-    lambda_list_kernel<false, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride,
-        (uint32_t)(((1ull << 32) + stride - 1) / stride), ctx->nl_count.p, role, want);
+    lambda_list_kernel<false, kCap><<<div_up(sel.bound, kBlock), kBlock, 0, ctx->stream>>>(
+        ctx->sc, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, inv_stride, ctx->nl_count.p);
   PBF_LAUNCH_CHECK(ctx);
   return PBF_OK;
 }
 
-template <int kCap> int launch_delta_cap(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted,
-                                         const uint32_t *table, const float4 *pstar_in, float4 *pstar_out,
-                                         const uint32_t *role, uint32_t want) {
+template <int kCap> int launch_delta_cap(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,
+                                         const float4 *pstar_in, float4 *pstar_out) {
   const uint32_t *nl4 = ctx->nl.p;
   if (ctx->flags & PBF_FLAG_STRICT_FP)
-    delta_list_kernel<true, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, first, count, keys_sorted, table, pstar_in, pstar_out, nl4, ctx->nl_stride, ctx->nl_count.p, role, want);
+    delta_list_kernel<true, kCap><<<div_up(sel.bound, kBlock), kBlock, 0, ctx->stream>>>(
+        ctx->sc, sel, keys_sorted, table, pstar_in, pstar_out, nl4, ctx->nl_stride, ctx->nl_count.p);
   else
-    delta_list_kernel<false, kCap><<<div_up(count, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, first, count, keys_sorted, table, pstar_in, pstar_out, nl4, ctx->nl_stride, ctx->nl_count.p, role, want);
+    delta_list_kernel<false, kCap><<<div_up(sel.bound, kBlock), kBlock, 0, ctx->stream>>>(
+        ctx->sc, sel, keys_sorted, table, pstar_in, pstar_out, nl4, ctx->nl_stride, ctx->nl_count.p);
   PBF_LAUNCH_CHECK(ctx);
   return PBF_OK;
 }
 
 }  // namespace
 
-int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                       const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
-                       const uint32_t *role, uint32_t want) {
-  if (count == 0) return PBF_OK;
+// The list spans the whole sorted array of the step: ctx->sc.n particles (slab path: the capacity of the local array,
+// fixed between re-plans, so the list is sized once and never re-allocated in mid-step).
+int launch_lambda_list(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,
+                       const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out) {
+  if (sel.bound == 0) return PBF_OK;
   const uint32_t n = ctx->sc.n;
   const uint32_t stride = (n + 31u) & ~31u;  // rows start on 128-byte boundaries
-  // Rows cost address space, not bandwidth (a row is touched only by particles with that many hits), so the thread-per-
-  // particle search keeps up to kListWide hits: while a dam break splashes, particles clamped onto the walls pile up
-  // (dam-1m after 30 steps: 431 particles with 97..229 neighbours) and every one that overflows drags its block through
-  // the one-pass fallback in both passes.  The wide list needs n < 2^32 / 193 = 22 M particles per device; above that
-  // the list is kListMax deep.
+  // Rows cost address space, not bandwidth (a row is touched only by particles with that many hits), so the search keeps
+  // up to kListWide hits: while a dam break splashes, particles clamped onto the walls pile up (dam-1m after 30 steps:
+  // 431 particles with 97..229 neighbours) and every one that overflows drags its block through the one-pass fallback
+  // in both passes.  The wide list needs n < 2^32 / 193 = 22 M particles per device; above that the list is kListMax deep.
   uint32_t cap = (uint32_t)ctx->list_cap;
   if (cap == kListWide && (uint64_t)stride * (kListWide + 1) >= (1ull << 32)) cap = kListMax;
   if ((uint64_t)stride * (cap + 1) >= (1ull << 32))
@@ -282,16 +273,16 @@ int launch_lambda_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint3
   ctx->nl_stride = stride;
   ctx->nl_cap = cap;
   if (cap == kListWide)
-    return launch_lambda_cap<kListWide>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
-  return launch_lambda_cap<kListMax>(ctx, first, count, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride, role, want);
+    return launch_lambda_cap<kListWide>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride);
+  return launch_lambda_cap<kListMax>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride);
 }
 
-int launch_delta_list(pbf_ctx *ctx, uint32_t first, uint32_t count, const uint32_t *keys_sorted, const uint32_t *table,
-                      const float4 *pstar_in, float4 *pstar_out, const uint32_t *role, uint32_t want) {
-  if (count == 0) return PBF_OK;
+int launch_delta_list(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,
+                      const float4 *pstar_in, float4 *pstar_out) {
+  if (sel.bound == 0) return PBF_OK;
   if (ctx->nl_cap == kListWide)  // the capacity the lambda pass of this iteration wrote the list with
-    return launch_delta_cap<kListWide>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
-  return launch_delta_cap<kListMax>(ctx, first, count, keys_sorted, table, pstar_in, pstar_out, role, want);
+    return launch_delta_cap<kListWide>(ctx, sel, keys_sorted, table, pstar_in, pstar_out);
+  return launch_delta_cap<kListMax>(ctx, sel, keys_sorted, table, pstar_in, pstar_out);
 }
 
 }  // namespace pbf

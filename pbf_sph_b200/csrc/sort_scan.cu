@@ -126,10 +126,11 @@ constexpr int kBins = 1 << kDigitBits;  // 1024
 constexpr int kPasses = 3;              // 30 bits
 
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n,
-                                                                 int shift, uint32_t n_tiles,
-                                                                 uint32_t *__restrict__ tile_hist,
+                                                                 const uint32_t *__restrict__ n_dev, int shift,
+                                                                 uint32_t n_tiles, uint32_t *__restrict__ tile_hist,
                                                                  uint32_t *__restrict__ digit_total) {
   __shared__ uint32_t hist[kBins];
+  if (n_dev) n = __ldg(n_dev);  // slab path: the pair count lives in device memory; tiles beyond it hold nothing
   for (int b = threadIdx.x; b < kBins; b += kSortThreads) hist[b] = 0;
   __syncthreads();
   const uint32_t base = blockIdx.x * kSortTile;
@@ -163,12 +164,17 @@ __global__ void __launch_bounds__(kSortThreads) sort_row_scan_kernel(uint32_t *_
 template <bool kIotaValues>
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t *__restrict__ keys_in,
                                                                     const uint32_t *__restrict__ vals_in, uint32_t n,
-                                                                    int shift, uint32_t n_tiles,
+                                                                    const uint32_t *__restrict__ n_dev, int shift,
+                                                                    uint32_t n_tiles,
                                                                     const uint32_t *__restrict__ tile_offsets,
                                                                     const uint32_t *__restrict__ digit_total,
                                                                     uint32_t *__restrict__ keys_out,
                                                                     uint32_t *__restrict__ vals_out) {
   __shared__ uint32_t wc[kSortWarps][kBins];  // per-warp digit counters, then per-warp global bases (32 KB)
+  if (n_dev) {
+    n = __ldg(n_dev);
+    if (blockIdx.x * kSortTile >= n) return;  // an empty tile of the capacity-sized grid (uniform for the block)
+  }
   for (int b = threadIdx.x; b < kSortWarps * kBins; b += kSortThreads) (&wc[0][0])[b] = 0;
   __syncthreads();
 
@@ -274,7 +280,7 @@ int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t
   return PBF_OK;
 }
 
-int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n, const uint32_t *vals_in) {
+int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n, const uint32_t *vals_in, const uint32_t *n_dev) {
   PhaseScope ps(ctx, PBF_PH_SORT);
   if (n == 0) { ctx->keys_sorted = ctx->key_a.p; ctx->perm = ctx->idx_a.p; return PBF_OK; }
   const uint32_t n_tiles = div_up(n, kSortTile);
@@ -290,15 +296,15 @@ int radix_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n, const ui
   for (int pass = 0; pass < kPasses; ++pass) {
     const int shift = pass * kDigitBits;
     uint32_t *totals = digit_total + pass * kBins;
-    sort_hist_kernel<<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, n, shift, n_tiles, ctx->sort_hist.p, totals);
+    sort_hist_kernel<<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, n, n_dev, shift, n_tiles, ctx->sort_hist.p, totals);
     PBF_LAUNCH_CHECK(ctx);
     sort_row_scan_kernel<<<kBins / kSortWarps, kSortThreads, 0, ctx->stream>>>(ctx->sort_hist.p, n_tiles);
     PBF_LAUNCH_CHECK(ctx);
     if (pass == 0 && !vals_in)
-      sort_scatter_kernel<true><<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, nullptr, n, shift, n_tiles,
+      sort_scatter_kernel<true><<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, nullptr, n, n_dev, shift, n_tiles,
                                                                            ctx->sort_hist.p, totals, dst_k, dst_v);
     else
-      sort_scatter_kernel<false><<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, src_v, n, shift, n_tiles,
+      sort_scatter_kernel<false><<<n_tiles, kSortThreads, 0, ctx->stream>>>(src_k, src_v, n, n_dev, shift, n_tiles,
                                                                             ctx->sort_hist.p, totals, dst_k, dst_v);
     PBF_LAUNCH_CHECK(ctx);
     src_k = dst_k;

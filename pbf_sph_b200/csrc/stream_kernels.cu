@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kBlock) predict_key_kernel(StepConst c, const 
                                                              const float4 *__restrict__ vel,
                                                              uint32_t *__restrict__ keys) {
   const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= c.n) return;
+  if (i >= count_of(c)) return;
   float v[3], ps[3];
   uint32_t key;
   predict(c, ldg4(pos + i), ldg4(vel + i), v, ps, key);
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kBlock) reorder_kernel(StepConst c, const uint
                                                          unsigned long long *__restrict__ ids_out,
                                                          float4 *__restrict__ pstar_out) {
   const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= c.n) return;
+  if (i >= count_of(c)) return;
   const uint32_t s = __ldg(perm + i);
   const float4 p = ldg4(pos_in + s);
   const float4 v = ldg4(vel_in + s);
@@ -122,10 +122,12 @@ __global__ void __launch_bounds__(kBlock) reorder_kernel(StepConst c, const uint
 // table[z] = lower_bound(keys_sorted, z): identical to the reference's serial sweep (sph.hpp:243-248) for
 // every z, including runs of empty cells, and balanced regardless of how the particles cluster.
 __global__ void __launch_bounds__(kBlock) cell_table_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t G,
-                                                            uint32_t *__restrict__ table) {
+                                                            uint32_t *__restrict__ table,
+                                                            const uint32_t *__restrict__ range_dev) {
   const uint32_t z = blockIdx.x * kBlock + threadIdx.x;
   if (z >= G) return;
   uint32_t lo = 0, hi = n;
+  if (range_dev) { lo = __ldg(range_dev); hi = lo + __ldg(range_dev + 1); }
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
     if (__ldg(keys + mid) < z) lo = mid + 1; else hi = mid;
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(kBlock) cell_table_kernel(const uint32_t *__re
 __global__ void __launch_bounds__(kBlock) finalise_kernel(StepConst c, const float4 *__restrict__ pstar,
                                                           float4 *__restrict__ pos, float4 *__restrict__ vel) {
   const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= c.n) return;
+  if (i >= count_of(c)) return;
   const float4 ps = ldg4(pstar + i);
   float4 p = pos[i];
   float4 v = vel[i];
@@ -191,10 +193,10 @@ int launch_reorder(pbf_ctx *ctx, const uint32_t *perm, const float4 *pos_in, con
   return PBF_OK;
 }
 
-int launch_cell_table(pbf_ctx *ctx, const uint32_t *keys_sorted, uint32_t *table) {
+int launch_cell_table(pbf_ctx *ctx, const uint32_t *keys_sorted, uint32_t *table, const uint32_t *range_dev) {
   if (ctx->sc.G == 0) return PBF_OK;
   PhaseScope ps(ctx, PBF_PH_CELL_TABLE);
-  cell_table_kernel<<<div_up(ctx->sc.G, kBlock), kBlock, 0, ctx->stream>>>(keys_sorted, ctx->sc.n, ctx->sc.G, table);
+  cell_table_kernel<<<div_up(ctx->sc.G, kBlock), kBlock, 0, ctx->stream>>>(keys_sorted, ctx->sc.n, ctx->sc.G, table, range_dev);
   PBF_LAUNCH_CHECK(ctx);
   return PBF_OK;
 }

@@ -128,9 +128,146 @@ class LocalGroup:
 
 
 # ------------------------------------------------------------------------------------------------- bench.py, N > 1
+def _new_rank(torch, dist, device, rank, world, flags):
+    """A SlabRank on a fresh NCCL communicator (rank 0 makes the id, torch.distributed carries it)."""
+    from . import scenes
+    idt = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(SlabRank.unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    return SlabRank(scenes.H, device, rank, world, bytes(idt.cpu().numpy().tobytes()), flags)
+
+
+def nccl_parity(torch, dist, device, rank, world, frames=6) -> dict:
+    """`frames` moving-wall frames of the stock two-cube scene (18 522 particles) on the N-rank NCCL group against the
+    same frames on one device (rank 0): particle order, positions, velocities and colours must agree bit for bit."""
+    from . import scenes
+    p, xs = scenes.two_cubes(20000, 4)
+    sr = _new_rank(torch, dist, device, rank, world, 0)
+    sr.set_replan(2)
+    sr.upload(shard(xs, rank, world))
+    for f in range(frames):
+        sr.step(scenes.apply_motion(p, f))
+    mine, st = sr.download(), sr.stats()
+    parts = [None] * world
+    dist.all_gather_object(parts, (mine.tobytes(), st["owned"], st["ghosts"]))
+    sr.close()
+    verdict = None
+    if rank == 0:
+        got = np.concatenate([np.frombuffer(b, dtype=PARTICLE) for b, _, _ in parts])
+        with Solver(scenes.H, device) as s:
+            s.upload(xs)
+            for f in range(frames):
+                s.step(scenes.apply_motion(p, f))
+            ref = s.download()
+        same = (len(ref) == len(got) and np.array_equal(ref["id"], got["id"])
+                and all(np.array_equal(ref[k].view(np.uint32), got[k].view(np.uint32)) for k in ("position", "velocity", "colour")))
+        verdict = {"nccl_vs_single": "bit-identical" if same else "MISMATCH", "ranks": world, "frames": frames,
+                   "scene": "stock two-cube scene, 18 522 particles, moving wall, 4 solver iterations, splits re-planned every 2 steps",
+                   "owned": [o for _, o, _ in parts], "ghosts": [g for _, _, g in parts]}
+    out = [verdict]
+    dist.broadcast_object_list(out, 0)
+    return out[0]
+
+
+def _timed_group_steps(torch, dist, sr, stream, p, steps):
+    """`steps` slab steps, barrier on both sides, CUDA events on the rank's stream, max over ranks -> ms total."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        sr.step(p)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def _profiled_group_steps(torch, dist, sr, p, steps, flags):
+    sr.s.set_flags(capi.FLAG_PROFILE | flags)
+    sr.s.profile_reset()
+    torch.cuda.synchronize()
+    dist.barrier()
+    for _ in range(steps):
+        sr.step(p)
+    torch.cuda.synchronize()
+    dist.barrier()
+    prof = sr.s.profile()
+    sr.s.set_flags(flags)
+    return prof
+
+
+def secondary_multi(torch, dist, args, device, rank, world, UNIT) -> list:
+    """BASELINE.json configs[2] (dam-8m split over the N GPUs: strong scaling) and configs[4] (dam-weak-8m: ~8 M particles
+    per GPU, 8 solver iterations: weak scaling), few steps each.  Rank 0 first measures the single-GPU figure each entry's
+    efficiency is quoted against (dam(200) with 4 and with 8 iterations) while the other ranks wait."""
+    from . import scenes
+    k = max(3, args.secondary_steps)
+    single = {}
+    if rank == 0:
+        p1, xs1 = scenes.dam_break(200, 4)
+        stream = torch.cuda.Stream()
+        with Solver(scenes.H, device, args.flags) as s:
+            s.set_stream(stream.cuda_stream)
+            s.upload(xs1)
+            del xs1
+            for _ in range(args.settle):
+                s.step(p1)
+            for iters in (4, 8):
+                p1.iteration = iters
+                for _ in range(3):
+                    s.step(p1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(k):
+                    s.step(p1)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                single[iters] = e0.elapsed_time(e1) / k
+    box = [single]
+    dist.broadcast_object_list(box, 0)
+    single = box[0]
+    out = []
+    for name, side, iters, scaling in (("dam-8m", 200, 4, "strong"),
+                                       ("dam-weak-8m", int(round((8_000_000 * world) ** (1 / 3))), 8, "weak")):
+        p, mine, n_total = scenes.dam_break_shard(side, iters, rank, world)
+        sr = _new_rank(torch, dist, device, rank, world, args.flags)
+        stream = torch.cuda.Stream()
+        sr.s.set_stream(stream.cuda_stream)
+        sr.upload(mine)
+        del mine
+        for _ in range(args.settle + 3):
+            sr.step(p)
+        ms = _timed_group_steps(torch, dist, sr, stream, p, k)
+        prof = _profiled_group_steps(torch, dist, sr, p, k, args.flags)
+        st = sr.stats()
+        ranks = [None] * world
+        dist.all_gather_object(ranks, {"rank": rank, "owned": st["owned"], "ghosts": st["ghosts"],
+                                       "ms": {f: round(v / k, 4) for f, v in prof["ms"].items() if v > 0}})
+        sr.close()
+        ms_step = ms / k
+        one = single[iters]  # dam(200) = 8 M particles on one GPU with the same iteration count
+        if scaling == "strong":
+            eff = one / (world * ms_step)
+        else:  # weak: per-GPU work ~ constant; compare particle-iterations/s per GPU with the single-GPU run
+            eff = (n_total * iters / ms_step / world) / (8_000_000 * iters / one)
+        out.append({"name": name, "workload": f"dam-break {side}^3 = {n_total} particles, {iters} solver iterations, {world} GPUs",
+                    "n_gpus": world, "scaling": scaling, "particles": n_total, "solver_iterations": iters, "steps": k,
+                    "settle_steps": args.settle, "ms_per_step": ms_step, "value": n_total * iters / (ms_step * 1e-3), "unit": UNIT,
+                    "single_gpu": {"workload": f"dam-break 200^3 = 8000000 particles, {iters} solver iterations", "ms_per_step": one,
+                                   "value": 8_000_000 * iters / (one * 1e-3)},
+                    "efficiency_vs_single_gpu": eff, "ranks": ranks})
+    return out
+
+
 def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> None:
     """One rank per GPU under torchrun: weak scaling (the dam-break block grows so that every GPU holds ~1 M
     particles), device time by CUDA events, max over ranks, rank 0 prints the JSON line."""
+    import sys
     import torch
     import torch.distributed as dist
     from . import scenes
@@ -139,14 +276,16 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    parity = nccl_parity(torch, dist, local, rank, world)
+    if parity["nccl_vs_single"] != "bit-identical":
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "n_gpus": world, "parity": parity, "error": "NCCL slab path differs from one device"}))
+        dist.destroy_process_group()
+        sys.exit(3)
     name, desc, p, xs = workload(args.workload, world)
     n_total, iters = len(xs), int(p.iteration)
 
-    idt = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(SlabRank.unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    sr = SlabRank(scenes.H, local, rank, world, bytes(idt.cpu().numpy().tobytes()), args.flags)
+    sr = _new_rank(torch, dist, local, rank, world, args.flags)
     stream = torch.cuda.Stream()
     sr.s.set_stream(stream.cuda_stream)
     mine = shard(xs, rank, world)
@@ -157,33 +296,13 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
     sr.s.sync()
     sr.s.profile_reset()
     l0 = sr.s.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    dist.barrier()
     # NVML queries go through the driver: one sampler (rank 0, 10 Hz) is enough and keeps the other ranks' launches quiet
     with ClockSampler(local, period=0.1, enabled=(rank == 0)) as clk:
-        e0.record(stream)
-        for _ in range(args.steps):
-            sr.step(p)
-        e1.record(stream)
-        torch.cuda.synchronize()
-    dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+        ms_total = _timed_group_steps(torch, dist, sr, stream, p, args.steps)
     launches = sr.s.launch_count() - l0
-    # the same steps again with the library's per-family CUDA events on (they cost ~2 % of a step, so `value` is
+    # the same steps again with the library's per-family CUDA events on (they stretch the step, so `value` is
     # timed without them): per-rank phase times and the roofline's launch durations
-    sr.s.set_flags(capi.FLAG_PROFILE | args.flags)
-    sr.s.profile_reset()
-    torch.cuda.synchronize()
-    dist.barrier()
-    for _ in range(args.steps):
-        sr.step(p)
-    torch.cuda.synchronize()
-    dist.barrier()
-    prof = sr.s.profile()
-    sr.s.set_flags(args.flags)
+    prof = _profiled_group_steps(torch, dist, sr, p, args.steps, args.flags)
     st = sr.stats()
 
     # end to end: every step uploads the rank's particles from pinned host memory and reads them back into it
@@ -222,10 +341,15 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
     dist.all_gather_object(gathered, {"rank": rank, **st, "launches": launches,
                                       "ms": {k: round(v / args.steps, 4) for k, v in prof["ms"].items() if v > 0}})
     clocks = clk.summary()
+    sr.close()
+    secondary = None
+    if not args.no_secondary and args.workload == "auto":
+        secondary = secondary_multi(torch, dist, args, local, rank, world, UNIT)
     if rank == 0:
         value = n_total * iters * args.steps / (ms_total * 1e-3)
         e2e_val = n_total * iters * e2e_steps / float(e2e_s.item())
         per_step_bytes = float(moved_t.item()) / e2e_steps * PARTICLE.itemsize
+        sums = [sum(v for k, v in g["ms"].items() if k != "diffuse") for g in gathered]
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -242,7 +366,8 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(per_step_bytes),
                     "d2h_bytes_per_step": int(per_step_bytes), "steps": e2e_steps,
                     "api": "pbf_dist_upload (host AoS) -> pbf_dist_step -> pbf_dist_download, every step, all ranks"},
-            "gpu_launches": int(sum(g["launches"] for g in gathered)), "ranks": gathered, "clocks": clocks,
+            "gpu_launches": int(sum(g["launches"] for g in gathered)), "parity": parity,
+            "rank_ms_spread": {"min": min(sums), "max": max(sums), "note": "per-rank sum of the kernel families (events pass), ms/step"},
+            "ranks": gathered, "clocks": clocks, "secondary": secondary,
         }))
-    sr.close()
     dist.destroy_process_group()

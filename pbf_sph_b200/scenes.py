@@ -69,6 +69,24 @@ def dam_break(side: int, iteration: int = 4, scale: float = 500.0):
     return p, xs
 
 
+def dam_break_shard(side: int, iteration: int, rank: int, world: int, scale: float = 500.0):
+    """Block `rank` of `world` of dam_break(side)'s particle array (the blocks dist.shard() cuts), generated directly:
+    a 64 M-particle array is 3.6 GB, which eight ranks should not each build in full."""
+    lx, ly = 44.0 * side + 200.0, 22.0 * side + 200.0
+    p = base_params(iteration, scale)
+    p.max_bound[:] = (lx, ly, ly)
+    n = side ** 3
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    i = np.arange(lo, hi, dtype=np.int64)
+    xs = np.zeros(hi - lo, PARTICLE)
+    lattice = np.stack([i // (side * side), (i // side) % side, i % side], axis=1).astype(np.float32)
+    xs["position"] = lattice * np.float32(22.0) + np.asarray((100.0, ly - 22.0 * side - 50.0, 100.0), np.float32)
+    xs["id"] = i.astype(np.uint64)
+    xs["mass"] = 1.0
+    xs["colour"] = np.asarray((0.0, 0.1, 0.8, 1.0), np.float32)
+    return p, xs, n
+
+
 WORKLOADS = {
     # name: (factory, kwargs) — BASELINE.json configs
     "ref-2cubes": lambda: two_cubes(20000, 6),

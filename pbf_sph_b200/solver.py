@@ -157,6 +157,11 @@ class Solver:
     def profile_reset(self) -> None:
         self._ck(self._L.pbf_profile_reset(self._ctx))
 
+    def profile_mask(self, families=None) -> None:
+        """Families timed under FLAG_PROFILE (names from capi.PHASES; None = all)."""
+        mask = 0xFFFFFFFF if families is None else sum(1 << capi.PHASES.index(f) for f in families)
+        self._ck(self._L.pbf_profile_set_mask(self._ctx, mask))
+
     def profile(self) -> dict:
         p = Profile()
         self._ck(self._L.pbf_profile_read(self._ctx, C.byref(p)))

@@ -63,5 +63,6 @@ def test_reference_arm_line(oracle_mod):
             "print(json.dumps(bench.reference_cpu(p, xs, 2, 1, settle_steps=2, budget_s=5.0)))\n")
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
-    pis, ms, cores, kind, sample = json.loads(out.stdout.strip().splitlines()[-1])
+    pis, ms, cores, kind, sample, same, n_timed = json.loads(out.stdout.strip().splitlines()[-1])
     assert pis > 0 and ms > 0 and cores >= 1 and kind in ("reference", "port") and "settled" in sample
+    assert isinstance(same, bool) and 0 < n_timed <= 16 ** 3
