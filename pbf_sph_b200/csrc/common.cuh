@@ -163,8 +163,10 @@ inline Sel sel_range(uint32_t first, uint32_t count) {
 template <typename T> struct DevBuf {
   T *p = nullptr;
   size_t cap = 0;
+  bool borrowed = false;  // points into memory owned elsewhere (the slab arena, dist.cu): never freed or re-allocated here
   cudaError_t reserve(size_t n, bool keep = false, cudaStream_t s = 0) {
     if (n <= cap) return cudaSuccess;
+    if (borrowed) return cudaErrorMemoryAllocation;  // the arena's capacity is fixed between plan steps
     size_t want = n + n / 8 + 256;
     T *q = nullptr;
     cudaError_t e = cudaMalloc(&q, want * sizeof(T));
@@ -180,9 +182,10 @@ template <typename T> struct DevBuf {
     return cudaSuccess;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && !borrowed) cudaFree(p);
     p = nullptr;
     cap = 0;
+    borrowed = false;
   }
 };
 
@@ -299,7 +302,8 @@ struct PhaseScope {
   pbf_ctx *ctx;
   int phase;
   int slot;
-  PhaseScope(pbf_ctx *c, int phase);
+  cudaStream_t stream;  // the stream the scope's work is enqueued on (default: the context's main stream)
+  PhaseScope(pbf_ctx *c, int phase, cudaStream_t on = nullptr);
   ~PhaseScope();
 };
 
@@ -357,6 +361,7 @@ int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t
 int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col);
 
 void dist_release(pbf_ctx *ctx);  // dist.cu
+int dist_refresh_counts(pbf_ctx *ctx);  // slab rank: wait for the last step and refresh ctx->n from the device-side counts
 // host <-> device plumbing of the drop-in calls (context.cu), shared with the multi-device drop-in call (dist.cu)
 int upload_device(pbf_ctx *ctx, const pbf_particle *xs, uint64_t n);  // async H2D + unpack on ctx->stream; sets ctx->n
 void host_pin(pbf_ctx *ctx, void *p, size_t bytes);                   // PBF_FLAG_PIN_HOST

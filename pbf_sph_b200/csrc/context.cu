@@ -102,7 +102,7 @@ static const char *const kPhaseNames[PBF_PH_COUNT] = {
     "advect+copy (predict_key)", "sortz (radix sort)", "sortz (reorder)", "gridtable", "sph-diffuse", "sph-lambda", "sph-delta",
     "sph-finalise", "mc-field", "mc_psum", "gpu_mc", "write back", "halo", "", "", ""};
 
-PhaseScope::PhaseScope(pbf_ctx *c, int ph) : ctx(c), phase(ph), slot(-1) {
+PhaseScope::PhaseScope(pbf_ctx *c, int ph, cudaStream_t on) : ctx(c), phase(ph), slot(-1), stream(on ? on : c->stream) {
   nvtxRangePushA(kPhaseNames[ph]);
   if (!(ctx->flags & PBF_FLAG_PROFILE) || !((ctx->prof_mask >> ph) & 1u)) return;
   if (!ctx->ev_created) {
@@ -114,12 +114,12 @@ PhaseScope::PhaseScope(pbf_ctx *c, int ph) : ctx(c), phase(ph), slot(-1) {
   ctx->ev_used += 2;
   ctx->ev_phase[slot] = phase;
   ctx->ev_launch0[slot] = ctx->launches;
-  cudaEventRecord(ctx->ev[slot], ctx->stream);
+  cudaEventRecord(ctx->ev[slot], stream);
 }
 PhaseScope::~PhaseScope() {
   nvtxRangePop();
   if (slot < 0) return;
-  cudaEventRecord(ctx->ev[slot + 1], ctx->stream);
+  cudaEventRecord(ctx->ev[slot + 1], stream);
   ctx->prof.launches[phase] += ctx->launches - ctx->ev_launch0[slot];
 }
 
@@ -532,6 +532,7 @@ int pbf_download(pbf_ctx *ctx, pbf_particle *xs, uint64_t capacity, uint64_t *n_
 
 int pbf_particle_count(pbf_ctx *ctx, uint64_t *n_out) {
   if (!ctx || !n_out) return fail(ctx, PBF_ERR_INVALID, "pbf_particle_count", "NULL");
+  if (ctx->dist) PBF_TRY(dist_refresh_counts(ctx));  // slab rank: the count lives on the device between plan steps
   *n_out = ctx->n;
   return PBF_OK;
 }
@@ -559,8 +560,9 @@ int pbf_grid(pbf_ctx *ctx, pbf_grid_info *out) {
 int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes) {
   PBF_ENTER(ctx);
   if (!dst) return fail(ctx, PBF_ERR_INVALID, "dst", "NULL");
+  if (ctx->dist) return fail(ctx, PBF_ERR_STATE, "pbf_debug_read", "taps are single-device (a slab rank's arrays are laid out by the arena)");
   PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const uint64_t n = ctx->dist ? ctx->sc.n : ctx->n;  // slab path: taps cover the local array (ghosts + owned)
+  const uint64_t n = ctx->n;
   const void *src = nullptr;
   uint64_t bytes = 0;
   bool strided_w = false;
