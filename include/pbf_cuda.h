@@ -167,7 +167,10 @@ enum {
   PBF_PH_MC_COUNT_SCAN = 9,
   PBF_PH_MC_EMIT = 10,
   PBF_PH_PACK = 11,
-  PBF_PH_HALO = 12,
+  PBF_PH_HALO = 12,            /* slab path: bookkeeping and exchange kernels (masks, counts, scans, pushes) */
+  PBF_PH_SLAB_SETUP = 13,      /* slab path, a SPAN: step start -> first solver iteration (phases A-E with their barriers) */
+  PBF_PH_SLAB_BARRIER = 14,    /* slab path: the cross-rank barriers (waiting for the slowest rank included) */
+  PBF_PH_SLAB_ITERATIONS = 15, /* slab path, a SPAN: the solver iterations with their halo exchanges, up to finalise */
   PBF_PH_COUNT = 16
 };
 typedef struct pbf_profile {

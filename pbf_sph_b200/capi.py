@@ -34,7 +34,7 @@ TAP_KEYS_INPUT, TAP_PERM, TAP_KEYS_SORTED, TAP_CELL_TABLE, TAP_CAND_COUNT, TAP_N
 TAP_LAMBDA, TAP_RHO, TAP_IDS, TAP_MC_FIELD, TAP_MC_COLOUR, TAP_LIST_HITS = range(6, 12)
 
 PHASES = ["predict_key", "sort", "reorder", "cell_table", "diffuse", "lambda", "delta", "finalise", "mc_field",
-          "mc_count_scan", "mc_emit", "pack", "halo"]
+          "mc_count_scan", "mc_emit", "pack", "halo", "slab_setup", "slab_barrier", "slab_iterations"]
 PH_COUNT = 16
 NCCL_ID_BYTES = 128
 

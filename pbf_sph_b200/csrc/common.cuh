@@ -298,6 +298,8 @@ void host_grid(float h, const pbf_params &p, pbf_grid_info &g);
 void host_step_const(float h, const pbf_params &p, const pbf_grid_info &g, uint32_t n, StepConst &sc);
 
 // phase profiling ---------------------------------------------------------------------------------------
+int prof_begin(pbf_ctx *ctx, int phase, cudaStream_t stream);  // -> event slot (or -1: not timed)
+void prof_end(pbf_ctx *ctx, int slot, cudaStream_t stream);
 struct PhaseScope {
   pbf_ctx *ctx;
   int phase;

@@ -100,27 +100,36 @@ void host_step_const(float h, const pbf_params &p, const pbf_grid_info &g, uint3
 // timeline of this backend reads like the reference's own "advance" breakdown.
 static const char *const kPhaseNames[PBF_PH_COUNT] = {
     "advect+copy (predict_key)", "sortz (radix sort)", "sortz (reorder)", "gridtable", "sph-diffuse", "sph-lambda", "sph-delta",
-    "sph-finalise", "mc-field", "mc_psum", "gpu_mc", "write back", "halo", "", "", ""};
+    "sph-finalise", "mc-field", "mc_psum", "gpu_mc", "write back", "halo", "slab-setup", "slab-barrier", "slab-iterations"};
 
-PhaseScope::PhaseScope(pbf_ctx *c, int ph, cudaStream_t on) : ctx(c), phase(ph), slot(-1), stream(on ? on : c->stream) {
-  nvtxRangePushA(kPhaseNames[ph]);
-  if (!(ctx->flags & PBF_FLAG_PROFILE) || !((ctx->prof_mask >> ph) & 1u)) return;
+// A timed span that does not fit a C++ scope (dist.cu: the pre-iteration part of a slab step): returns the event slot, or -1.
+int prof_begin(pbf_ctx *ctx, int ph, cudaStream_t stream) {
+  if (!(ctx->flags & PBF_FLAG_PROFILE) || !((ctx->prof_mask >> ph) & 1u)) return -1;
   if (!ctx->ev_created) {
     for (int i = 0; i < pbf_ctx::kMaxEv; ++i) cudaEventCreate(&ctx->ev[i]);
     ctx->ev_created = true;
   }
-  if (ctx->ev_used + 2 > pbf_ctx::kMaxEv) return;  // full: this scope goes untimed until the next read
-  slot = ctx->ev_used;
+  if (ctx->ev_used + 2 > pbf_ctx::kMaxEv) return -1;  // full: this span goes untimed until the next read
+  const int slot = ctx->ev_used;
   ctx->ev_used += 2;
-  ctx->ev_phase[slot] = phase;
+  ctx->ev_phase[slot] = ph;
   ctx->ev_launch0[slot] = ctx->launches;
   cudaEventRecord(ctx->ev[slot], stream);
+  return slot;
+}
+void prof_end(pbf_ctx *ctx, int slot, cudaStream_t stream) {
+  if (slot < 0) return;
+  cudaEventRecord(ctx->ev[slot + 1], stream);
+  ctx->prof.launches[ctx->ev_phase[slot]] += ctx->launches - ctx->ev_launch0[slot];
+}
+
+PhaseScope::PhaseScope(pbf_ctx *c, int ph, cudaStream_t on) : ctx(c), phase(ph), slot(-1), stream(on ? on : c->stream) {
+  nvtxRangePushA(kPhaseNames[ph]);
+  slot = prof_begin(ctx, ph, stream);
 }
 PhaseScope::~PhaseScope() {
   nvtxRangePop();
-  if (slot < 0) return;
-  cudaEventRecord(ctx->ev[slot + 1], stream);
-  ctx->prof.launches[phase] += ctx->launches - ctx->ev_launch0[slot];
+  prof_end(ctx, slot, stream);
 }
 
 static void profile_collect(pbf_ctx *ctx) {
@@ -333,6 +342,9 @@ int pbf_create(pbf_ctx **out, float h, int device) {
   ctx->h = h;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+#ifdef PBF_L2_GRAN
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, PBF_L2_GRAN);
+#endif
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);

@@ -659,7 +659,7 @@ int barrier(std::vector<pbf_ctx *> &L, int which) {
   if (!d0->local_mode) {
     pbf_ctx *c = L[0];
     cudaStream_t st = which ? d0->comm_stream : c->stream;
-    PhaseScope ps(c, PBF_PH_HALO, st);
+    PhaseScope ps(c, PBF_PH_SLAB_BARRIER, st);
     PBF_NCCL(c, g_nccl.AllReduce(d0->bar_word, d0->bar_word, 1, ncclUint32, ncclSum, d0->comm, st));
     return PBF_OK;
   }
@@ -1175,6 +1175,11 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
       PBF_TRY(build_arenas(L, std::max(cap_g, 1u), std::max(cap_own, 1u), live));
     }
   }
+  std::vector<int> span(L.size(), -1);
+  for (size_t r = 0; r < L.size(); ++r) {
+    PBF_CUDA(L[r], cudaSetDevice(L[r]->device));
+    span[r] = prof_begin(L[r], PBF_PH_SLAB_SETUP, L[r]->stream);
+  }
   for (pbf_ctx *c : L) PBF_TRY(phase_a(c, p, replan));
   if (replan) {
     PBF_TRY(all_reduce_sum_u32(L, [](pbf_ctx *c) { return c->dist->d_hist.p; }, L[0]->dist->hist_buckets));
@@ -1264,6 +1269,11 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
   for (pbf_ctx *c : L) PBF_TRY(phase_d(c));
   PBF_TRY(barrier(L, 0));
   for (pbf_ctx *c : L) PBF_TRY(phase_e(c));
+  for (size_t r = 0; r < L.size(); ++r) {
+    PBF_CUDA(L[r], cudaSetDevice(L[r]->device));
+    prof_end(L[r], span[r], L[r]->stream);
+    span[r] = prof_begin(L[r], PBF_PH_SLAB_ITERATIONS, L[r]->stream);
+  }
 
   for (uint64_t it = 0; it < p.iteration; ++it) {
     const bool exchange = W > 1 && it + 1 < p.iteration;
@@ -1305,6 +1315,10 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
         PBF_LAUNCH_CHECK(c);
       }
     }
+  }
+  for (size_t r = 0; r < L.size(); ++r) {
+    PBF_CUDA(L[r], cudaSetDevice(L[r]->device));
+    prof_end(L[r], span[r], L[r]->stream);
   }
   for (pbf_ctx *c : L) {
     D *d = c->dist;

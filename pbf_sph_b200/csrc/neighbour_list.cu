@@ -21,6 +21,8 @@
 // The list keeps the candidates in the reference's visiting order, so every sum is formed in the reference's
 // order (sph.hpp:215-236).  A particle with more than kCap hits (particles piled into one cell) is flagged and
 // handled by the one-pass code in both passes.
+#include <algorithm>
+
 #include "cells.cuh"
 #include "common.cuh"
 #include "pair_math.cuh"
@@ -30,19 +32,48 @@ namespace pbf {
 namespace {
 
 #ifndef PBF_NL_BLOCK
-#define PBF_NL_BLOCK 128
+#define PBF_NL_BLOCK 256
 #endif
-#ifndef PBF_NL_MINB
-#define PBF_NL_MINB 1
+constexpr int kBlock = PBF_NL_BLOCK;  // lambda pass, launches below kLargeLaunch particles
+constexpr int kBlockD = 128;          // delta pass (larger blocks measured slower at every size)
+#ifndef PBF_NL_ST
+#define PBF_NL_ST ".cs"
 #endif
-constexpr int kBlock = PBF_NL_BLOCK;
+#ifndef PBF_NL_LDQ
+#define PBF_NL_LDQ ".cs"
+#endif
+
+// Candidate-position gather of the search loop.  PBF_NL_PF (64 / 128 / 256): L2 prefetch-size hint — a miss brings the
+// whole 128-byte line (eight positions of the same run) from DRAM instead of one 32-byte sector.
+__device__ __forceinline__ float4 ldg4s(const float4 *p) {
+#ifdef PBF_NL_GQ  /* cache qualifiers of the gather, e.g. ".nc.L1::evict_last" */
+  float4 v;
+  asm("ld.global" PBF_NL_GQ ".v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#elif defined(PBF_NL_PF)
+#define PBF_STR2(x) #x
+#define PBF_STR(x) PBF_STR2(x)
+  float4 v;
+  asm("ld.global.nc.L2::" PBF_STR(PBF_NL_PF) "B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+
+// list entry load (coherent — never .nc: the lambda kernel reads what it wrote itself)
+__device__ __forceinline__ uint32_t ld_list(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global" PBF_NL_LDQ ".b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // Predicated 32-bit global store (one @p STG, no divergent branch: with ~1 hit in 5 candidates some lane would take
 // a branch for most candidates anyway).  Streaming (.cs): the list is written once and read once per pass; it must not
 // push the 16 B/particle pStar array — which every candidate test gathers from — out of L2.
 __device__ __forceinline__ void store_if(uint32_t *p, uint32_t v, bool pred) {
   asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.b32 [%0], %1;\n\t}" ::"l"(p), "r"(v),
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global" PBF_NL_ST ".b32 [%0], %1;\n\t}" ::"l"(p), "r"(v),
       "r"((uint32_t)pred)
       : "memory");
 }
@@ -52,7 +83,7 @@ __device__ __forceinline__ void store_if(uint32_t *p, uint32_t v, bool pred) {
 // and an add on top of the store).
 __device__ __forceinline__ void append_if(uint32_t *nl, uint32_t &slot, uint32_t v, uint32_t stride, bool pred) {
   asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.cs.b32 [%1], %2;\n\t@q add.u32 %0, %0, %4;\n\t}"
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global" PBF_NL_ST ".b32 [%1], %2;\n\t@q add.u32 %0, %0, %4;\n\t}"
       : "+r"(slot)
       : "l"(nl + slot), "r"(v), "r"((uint32_t)pred), "r"(stride)
       : "memory");
@@ -62,7 +93,7 @@ __device__ __forceinline__ void append_if(uint32_t *nl, uint32_t &slot, uint32_t
 // then kW position gathers in flight), then ONE masked batch for the 1..kW-1 hits left over — a scalar remainder loop
 // waits out two dependent latencies (list entry, then position) per hit.  kW = 8 in the delta pass; 4 in the lambda
 // pass, whose search loop needs the registers (56 -> 9 blocks per SM).
-template <int kW, typename Acc>
+template <int kW, bool kSameKernel, typename Acc>
 __device__ __forceinline__ void sum_over_hits(Acc &acc, const StepConst &c, const float4 pa, const float4 *__restrict__ pstar,
                                               const uint32_t *row, uint32_t stride, uint32_t k, uint32_t self) {
   uint32_t i = 0;
@@ -70,7 +101,7 @@ __device__ __forceinline__ void sum_over_hits(Acc &acc, const StepConst &c, cons
     uint32_t b[kW];
     float4 q[kW];
 #pragma unroll
-    for (int m = 0; m < kW; ++m) b[m] = __ldcs(row + m * stride);
+    for (int m = 0; m < kW; ++m) b[m] = ld_list(row + m * stride);
 #pragma unroll
     for (int m = 0; m < kW; ++m) q[m] = ldg4(pstar + b[m]);
 #pragma unroll
@@ -81,7 +112,8 @@ __device__ __forceinline__ void sum_over_hits(Acc &acc, const StepConst &c, cons
     uint32_t b[kW - 1];
     float4 q[kW - 1];
 #pragma unroll
-    for (int m = 0; m < kW - 1; ++m) b[m] = (uint32_t)m < left ? __ldcs(row + m * stride) : self;
+    for (int m = 0; m < kW - 1; ++m)
+      b[m] = (uint32_t)m < left ? ld_list(row + m * stride) : self;
 #pragma unroll
     for (int m = 0; m < kW - 1; ++m) q[m] = ldg4(pstar + b[m]);
 #pragma unroll
@@ -113,16 +145,11 @@ __device__ __forceinline__ RowRuns load_row(const uint32_t *__restrict__ table, 
 }
 
 template <bool kStrict, int kCap>
-__global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepConst c, Sel sel,
-                                                             const uint32_t *__restrict__ keys,
-                                                             const uint32_t *__restrict__ table,
-                                                             const float4 *__restrict__ pos_mass,
-                                                             const float4 *__restrict__ pstar_in,
-                                                             float4 *__restrict__ pstar_out, float *__restrict__ rho_out,
-                                                             uint32_t *nl, uint32_t stride, uint32_t inv_stride,
-                                                             uint32_t *__restrict__ n_hits) {
-  uint32_t a;
-  if (!sel_particle(sel, blockIdx.x * kBlock + threadIdx.x, a)) return;
+__device__ __forceinline__ void lambda_particle(const StepConst &c, const uint32_t a, const uint32_t *__restrict__ keys,
+                                                const uint32_t *__restrict__ table, const float4 *__restrict__ pos_mass,
+                                                const float4 *__restrict__ pstar_in, float4 *__restrict__ pstar_out,
+                                                float *__restrict__ rho_out, uint32_t *nl, uint32_t stride, uint32_t inv_stride,
+                                                uint32_t *__restrict__ n_hits) {
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t key = __ldg(keys + a);
   const float mass = __ldg(&pos_mass[a].w);
@@ -149,7 +176,7 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
       // clamped into the run), where a scalar remainder loop waits out one gather latency per candidate.
       uint32_t b = s;
       for (; b + 4u <= e; b += 4u) {
-        const float4 q0 = ldg4(pstar_in + b), q1 = ldg4(pstar_in + b + 1), q2 = ldg4(pstar_in + b + 2), q3 = ldg4(pstar_in + b + 3);
+        const float4 q0 = ldg4s(pstar_in + b), q1 = ldg4s(pstar_in + b + 1), q2 = ldg4s(pstar_in + b + 2), q3 = ldg4s(pstar_in + b + 3);
         append_if(nl, slot, b, stride, LambdaAcc<kStrict>::test(c, pa, q0));
         append_if(nl, slot, b + 1u, stride, LambdaAcc<kStrict>::test(c, pa, q1));
         append_if(nl, slot, b + 2u, stride, LambdaAcc<kStrict>::test(c, pa, q2));
@@ -157,7 +184,7 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
       }
       if (b < e) {
         const uint32_t last = e - 1u;
-        const float4 q0 = ldg4(pstar_in + b), q1 = ldg4(pstar_in + min(b + 1u, last)), q2 = ldg4(pstar_in + min(b + 2u, last));
+        const float4 q0 = ldg4s(pstar_in + b), q1 = ldg4s(pstar_in + min(b + 1u, last)), q2 = ldg4s(pstar_in + min(b + 2u, last));
         append_if(nl, slot, b, stride, LambdaAcc<kStrict>::test(c, pa, q0));
         append_if(nl, slot, b + 1u, stride, b + 1u < e && LambdaAcc<kStrict>::test(c, pa, q1));
         append_if(nl, slot, b + 2u, stride, b + 2u < e && LambdaAcc<kStrict>::test(c, pa, q2));
@@ -165,7 +192,7 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
     } else {
 #pragma unroll 1
       for (uint32_t b = s; b < e; ++b) {
-        const bool hit = LambdaAcc<kStrict>::test(c, pa, ldg4(pstar_in + b));
+        const bool hit = LambdaAcc<kStrict>::test(c, pa, ldg4s(pstar_in + b));
         const bool fits = hit && k < (uint32_t)kCap;
         store_if(nl + slot, b, fits);
         slot += fits ? stride : 0u;
@@ -191,7 +218,7 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
   acc.init();
   acc.set_mass(mass);
   if (k <= (uint32_t)kCap) {
-    sum_over_hits<4>(acc, c, pa, pstar_in, nl + a, stride, k, a);
+    sum_over_hits<4, true>(acc, c, pa, pstar_in, nl + a, stride, k, a);
   } else {
     for_each_candidate(key, c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
@@ -201,54 +228,90 @@ __global__ void __launch_bounds__(kBlock, PBF_NL_MINB) lambda_list_kernel(StepCo
   if (rho_out) rho_out[a] = rho;
 }
 
-template <bool kStrict, int kCap>
-__global__ void __launch_bounds__(kBlock, 8) delta_list_kernel(StepConst c, Sel sel,
-                                                            const uint32_t *__restrict__ keys,
-                                                            const uint32_t *__restrict__ table,
-                                                            const float4 *__restrict__ pstar_in,
-                                                            float4 *__restrict__ pstar_out,
-                                                            const uint32_t *__restrict__ nl, uint32_t stride,
-                                                            const uint32_t *__restrict__ n_hits) {
+#define PBF_LAMBDA_ARGS                                                                                                  \
+  const uint32_t *__restrict__ keys, const uint32_t *__restrict__ table, const float4 *__restrict__ pos_mass,            \
+      const float4 *__restrict__ pstar_in, float4 *__restrict__ pstar_out, float *__restrict__ rho_out, uint32_t *nl,    \
+      uint32_t stride, uint32_t inv_stride, uint32_t *__restrict__ n_hits
+
+// One thread per particle, kB threads per block.  The block size sets how well the warps of an SM share their gathers in
+// L1: the hardware deals consecutive blocks to different SMs, so with 128-thread blocks the nine blocks of an SM work on
+// nine unrelated neighbourhoods, while the 32 warps of a 1 024-thread block sweep 1 024 consecutive particles (a compact
+// Morton block of ~160 cells) in step.  While the arrays fit the L2 an L1 miss is cheap and small blocks win (no idle
+// tail inside a block, finer waves); from ~3 M particles on (16 B x n of positions beyond what the L2 keeps beside the
+// list traffic) the extra misses go to DRAM and the large block is 17 % faster (profiles/r02b_block_size.txt).
+template <bool kStrict, int kCap, int kB>
+__global__ void __launch_bounds__(kB, 9 * 128 / kB < 1 ? 1 : 9 * 128 / kB) lambda_list_kernel(StepConst c, Sel sel, PBF_LAMBDA_ARGS) {
   uint32_t a;
-  if (!sel_particle(sel, blockIdx.x * kBlock + threadIdx.x, a)) return;
+  if (!sel_particle(sel, blockIdx.x * kB + threadIdx.x, a)) return;
+  lambda_particle<kStrict, kCap>(c, a, keys, table, pos_mass, pstar_in, pstar_out, rho_out, nl, stride, inv_stride, n_hits);
+}
+
+template <bool kStrict, int kCap>
+__device__ __forceinline__ void delta_particle(const StepConst &c, const uint32_t a, const uint32_t *__restrict__ keys,
+                                               const uint32_t *__restrict__ table, const float4 *__restrict__ pstar_in,
+                                               float4 *__restrict__ pstar_out, const uint32_t *__restrict__ nl, uint32_t stride,
+                                               const uint32_t *__restrict__ n_hits) {
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t k = __ldg(n_hits + a);
   DeltaAcc<kStrict> acc;
   acc.init();
   if (k <= (uint32_t)kCap) {
-    sum_over_hits<8>(acc, c, pa, pstar_in, nl + a, stride, k, a);  // add_in skips the particle itself (r < EPSILON)
+    sum_over_hits<8, false>(acc, c, pa, pstar_in, nl + a, stride, k, a);  // add_in skips the particle itself (r < EPSILON)
   } else {
     for_each_candidate(__ldg(keys + a), c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
   pstar_out[a] = acc.finish(c, pa);
 }
 
+#define PBF_DELTA_ARGS                                                                                                   \
+  const uint32_t *__restrict__ keys, const uint32_t *__restrict__ table, const float4 *__restrict__ pstar_in,            \
+      float4 *__restrict__ pstar_out, const uint32_t *__restrict__ nl, uint32_t stride, const uint32_t *__restrict__ n_hits
+
+template <bool kStrict, int kCap>
+__global__ void __launch_bounds__(kBlockD, 8) delta_list_kernel(StepConst c, Sel sel, PBF_DELTA_ARGS) {
+  uint32_t a;
+  if (!sel_particle(sel, blockIdx.x * kBlockD + threadIdx.x, a)) return;
+  delta_particle<kStrict, kCap>(c, a, keys, table, pstar_in, pstar_out, nl, stride, n_hits);
+}
+
+// particles per launch from which the 1 024-thread block pays (see lambda_list_kernel)
+constexpr uint32_t kLargeLaunch = 3000000u;
+
+template <bool kStrict, int kCap> int launch_lambda_mode(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted,
+                                                         const uint32_t *table, const float4 *pos_mass, const float4 *pstar_in,
+                                                         float4 *pstar_out, float *rho_out, uint32_t stride) {
+  uint32_t *nl4 = ctx->nl.p;
+  const uint32_t inv_stride = (uint32_t)(((1ull << 32) + stride - 1) / stride);
+  if (sel.bound >= kLargeLaunch)
+    lambda_list_kernel<kStrict, kCap, 1024><<<div_up(sel.bound, 1024u), 1024, 0, ctx->stream>>>(
+        ctx->sc, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, inv_stride, ctx->nl_count.p);
+  else
+    lambda_list_kernel<kStrict, kCap, kBlock><<<div_up(sel.bound, (uint32_t)kBlock), kBlock, 0, ctx->stream>>>(
+        ctx->sc, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, inv_stride, ctx->nl_count.p);
+  PBF_LAUNCH_CHECK(ctx);
+  return PBF_OK;
+}
+
 template <int kCap> int launch_lambda_cap(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,
                                           const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
                                           uint32_t stride) {
-  uint32_t *nl4 = ctx->nl.p;
-  const uint32_t inv_stride = (uint32_t)(((1ull << 32) + stride - 1) / stride);
   if (ctx->flags & PBF_FLAG_STRICT_FP)
-    lambda_list_kernel<true, kCap><<<div_up(sel.bound, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, inv_stride, ctx->nl_count.p);
-  else
-    lambda_list_kernel<false, kCap><<<div_up(sel.bound, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, inv_stride, ctx->nl_count.p);
+    return launch_lambda_mode<true, kCap>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride);
+  return launch_lambda_mode<false, kCap>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride);
+}
+
+template <bool kStrict, int kCap> int launch_delta_mode(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted,
+                                                        const uint32_t *table, const float4 *pstar_in, float4 *pstar_out) {
+  delta_list_kernel<kStrict, kCap><<<div_up(sel.bound, kBlockD), kBlockD, 0, ctx->stream>>>(
+      ctx->sc, sel, keys_sorted, table, pstar_in, pstar_out, ctx->nl.p, ctx->nl_stride, ctx->nl_count.p);
   PBF_LAUNCH_CHECK(ctx);
   return PBF_OK;
 }
 
 template <int kCap> int launch_delta_cap(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,
                                          const float4 *pstar_in, float4 *pstar_out) {
-  const uint32_t *nl4 = ctx->nl.p;
-  if (ctx->flags & PBF_FLAG_STRICT_FP)
-    delta_list_kernel<true, kCap><<<div_up(sel.bound, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, sel, keys_sorted, table, pstar_in, pstar_out, nl4, ctx->nl_stride, ctx->nl_count.p);
-  else
-    delta_list_kernel<false, kCap><<<div_up(sel.bound, kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, sel, keys_sorted, table, pstar_in, pstar_out, nl4, ctx->nl_stride, ctx->nl_count.p);
-  PBF_LAUNCH_CHECK(ctx);
-  return PBF_OK;
+  if (ctx->flags & PBF_FLAG_STRICT_FP) return launch_delta_mode<true, kCap>(ctx, sel, keys_sorted, table, pstar_in, pstar_out);
+  return launch_delta_mode<false, kCap>(ctx, sel, keys_sorted, table, pstar_in, pstar_out);
 }
 
 }  // namespace

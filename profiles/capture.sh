@@ -1,11 +1,11 @@
 #!/usr/bin/env bash
-# profiles/capture.sh <tag> — run on a B200 box (under gpurun): plain bench, ncu launch list of the same command,
+# [WORKLOAD=dam-8m] profiles/capture.sh <tag> — run on a B200 box (under gpurun): plain bench, ncu launch list of the same command,
 # one `ncu --set full` capture of the solver-iteration kernels.  Outputs land in gpurun_out/<tag>_*.
 set -u
 TAG=${1:-rXX}
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="python bench.py --steps 3 --warmup 3 --settle 30 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 3 --warmup 3 --settle 30 --no-cpu-baseline --no-e2e --no-secondary --workload ${WORKLOAD:-dam-1m}"
 $CMD > $OUT/${TAG}_plain.json 2> $OUT/${TAG}_plain.err || { echo "plain run failed"; tail -5 $OUT/${TAG}_plain.err; exit 1; }
 # launch list: skip the settle+warm-up launches, list the 3 timed steps
 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-900} -c ${COUNT:-120} --csv \
