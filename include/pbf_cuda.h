@@ -240,6 +240,11 @@ int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes);
  * compiled depth).  A particle with more hits than the depth takes the one-pass 27-cell walk in both solver passes; the
  * tests use the shallow list to drive that path on moderately dense clumps. */
 int pbf_debug_set_list_capacity(pbf_ctx *ctx, uint32_t hits);
+/* Parity tests only: the device exclusive prefix sum (csrc/sort_scan.cu; every compaction of the step — marching-cubes
+ * triangle offsets ompsph.hpp:359-397, drains, the slab path's send lists — goes through it) and the stable radix sort of
+ * (key, index) pairs over key bits [0, 30) (the std::sort of ompsph.hpp:158), on HOST arrays: in -> device -> out. */
+int pbf_debug_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint64_t n, uint32_t *out, uint32_t *total_out);
+int pbf_debug_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n, uint32_t *keys_out, uint32_t *perm_out);
 int pbf_profile_reset(pbf_ctx *ctx);
 int pbf_profile_read(pbf_ctx *ctx, pbf_profile *out);
 /* Families timed under PBF_FLAG_PROFILE: bit f = PBF_PH_f (default: all).  Every timed launch costs two event records

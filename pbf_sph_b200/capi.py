@@ -126,7 +126,7 @@ EXPORTS = [
     "pbf_advance_host", "pbf_advance_scene_host", "pbf_unpin_host", "pbf_query_result", "pbf_set_scene", "pbf_mesh_download",
     "pbf_mesh_device", "pbf_upload",
     "pbf_step", "pbf_sync", "pbf_download",
-    "pbf_particle_count", "pbf_device_state", "pbf_grid", "pbf_debug_read", "pbf_debug_set_list_capacity", "pbf_profile_reset", "pbf_profile_read", "pbf_profile_set_mask",
+    "pbf_particle_count", "pbf_device_state", "pbf_grid", "pbf_debug_read", "pbf_debug_set_list_capacity", "pbf_debug_scan_u32", "pbf_debug_sort_pairs", "pbf_profile_reset", "pbf_profile_read", "pbf_profile_set_mask",
     "pbf_launch_count", "pbf_dist_unique_id", "pbf_dist_init", "pbf_dist_init_local", "pbf_dist_upload",
     "pbf_dist_step", "pbf_dist_advance_host", "pbf_dist_download", "pbf_dist_set_replan", "pbf_dist_stats_read", "pbf_host_alloc", "pbf_host_free", "pbf_host_grid",
     "pbf_host_plan_splits", "pbf_host_work_weights", "pbf_host_constants", "pbf_host_morton_encode", "pbf_host_morton_decode",
@@ -176,6 +176,8 @@ def lib() -> C.CDLL:
         "pbf_grid": ([vp, P(GridInfo)], i32),
         "pbf_debug_read": ([vp, i32, vp, u64], i32),
         "pbf_debug_set_list_capacity": ([vp, u32], i32),
+        "pbf_debug_scan_u32": ([vp, vp, u64, vp, P(u32)], i32),
+        "pbf_debug_sort_pairs": ([vp, vp, u32, vp, vp], i32),
         "pbf_profile_reset": ([vp], i32),
         "pbf_profile_read": ([vp, P(Profile)], i32),
         "pbf_profile_set_mask": ([vp, u32], i32),

@@ -139,14 +139,19 @@ __device__ __forceinline__ uint32_t count_of(const StepConst &c) { return c.n_dy
 //     first + t          for t < count           (a contiguous range of the sorted array), then
 //     idx[t - count]     for t - count < n_idx   (a compacted index list: ring-1 ghosts, boundary / interior particles)
 // On the slab path count / n_idx are read from device memory (count_dev / n_idx_dev) and `bound` sizes the grid.
+// `skip` (slab path: the interior delta pass) drops the particles of the range whose skip[t] != 0 — the range stays in
+// place, so a warp's particles keep their 128-byte alignment (a compacted interior list shifted every warp off its lines).
 struct Sel {
   uint32_t first = 0, count = 0, n_idx = 0;
-  const uint32_t *count_dev = nullptr, *idx = nullptr, *n_idx_dev = nullptr;
+  const uint32_t *count_dev = nullptr, *idx = nullptr, *n_idx_dev = nullptr, *skip = nullptr;
   uint32_t bound = 0;  // host-side upper bound of count + n_idx
 };
 __device__ __forceinline__ bool sel_particle(const Sel &s, uint32_t t, uint32_t &a) {
   const uint32_t count = s.count_dev ? __ldg(s.count_dev) : s.count;
-  if (t < count) { a = s.first + t; return true; }
+  if (t < count) {
+    a = s.first + t;
+    return !(s.skip && __ldg(s.skip + t) != 0u);
+  }
   if (!s.idx) return false;
   const uint32_t k = t - count;
   if (k >= (s.n_idx_dev ? __ldg(s.n_idx_dev) : s.n_idx)) return false;

@@ -610,6 +610,41 @@ int pbf_debug_set_list_capacity(pbf_ctx *ctx, uint32_t hits) {
   return PBF_OK;
 }
 
+int pbf_debug_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint64_t n, uint32_t *out, uint32_t *total_out) {
+  PBF_ENTER(ctx);
+  if ((!in || !out) && n) return fail(ctx, PBF_ERR_INVALID, "pbf_debug_scan_u32", "NULL array");
+  DevBuf<uint32_t> buf;
+  PBF_CUDA(ctx, buf.reserve(n + 1));
+  PBF_CUDA(ctx, cudaMemcpyAsync(buf.p, in, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = exclusive_scan_u32(ctx, buf.p, buf.p, n, buf.p + n);
+  if (rc == PBF_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, buf.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && total_out) e = cudaMemcpyAsync(total_out, buf.p + n, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, PBF_ERR_CUDA, "pbf_debug_scan_u32", cudaGetErrorString(e));
+  }
+  buf.release();
+  return rc;
+}
+
+int pbf_debug_sort_pairs(pbf_ctx *ctx, const uint32_t *keys_in, uint32_t n, uint32_t *keys_out, uint32_t *perm_out) {
+  PBF_ENTER(ctx);
+  if ((!keys_in || !keys_out || !perm_out) && n) return fail(ctx, PBF_ERR_INVALID, "pbf_debug_sort_pairs", "NULL array");
+  if (n == 0) return PBF_OK;
+  DevBuf<uint32_t> buf;
+  PBF_CUDA(ctx, buf.reserve(n));
+  PBF_CUDA(ctx, cudaMemcpyAsync(buf.p, keys_in, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = radix_sort_pairs(ctx, buf.p, n);
+  if (rc == PBF_OK) {
+    cudaError_t e = cudaMemcpyAsync(keys_out, ctx->keys_sorted, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(perm_out, ctx->perm, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, PBF_ERR_CUDA, "pbf_debug_sort_pairs", cudaGetErrorString(e));
+  }
+  buf.release();
+  return rc;
+}
+
 int pbf_profile_reset(pbf_ctx *ctx) {
   PBF_ENTER(ctx);
   profile_collect(ctx);

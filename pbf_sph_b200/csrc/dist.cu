@@ -102,7 +102,7 @@ struct SlabDyn {
   uint32_t n_own;        // owned after migration
   uint32_t n_glo, n_ghi, n_local, first_local;  // ghosts below / above; local array = [first_local, first_local + n_local)
   uint32_t n_send;       // owned particles other ranks hold as ghosts, counted once per destination
-  uint32_t n_ring1, n_boundary, n_interior;
+  uint32_t n_ring1, n_boundary;
   uint32_t any_outside;  // some particle (on any rank) is predicted outside the grid (key >= G)
   uint32_t overflow;     // bit 0: held / owned particles, bit 1: ghost slots, bit 2: send lists — a capacity was exceeded
   uint32_t own_range[2];    // {own_off, n_own}
@@ -159,10 +159,11 @@ struct pbf_dist_state {
   // device scratch
   SlabDyn *dyn = nullptr, *h_dyn = nullptr;       // device / pinned mirror (valid after a stream sync)
   DevBuf<uint32_t> d_splits, d_row, d_hist, d_scratch;
-  DevBuf<uint32_t> mask, send_idx, leave_idx, blk_cnt, v2, role, role_cnt, ring1_idx, bnd_idx, int_idx;
+  DevBuf<uint32_t> mask, send_idx, leave_idx, blk_cnt, v2, role, role_cnt, ring1_idx, bnd_idx;
   DevBuf<float4> pstar1;
   bool diffuse_pending = false;
   uint32_t cnt_nblk = 0;                          // tile stride of blk_cnt as its last count pass wrote it (the arena may grow before the scatter)
+  uint32_t kept_nblk = 0;                         // tiles of the kept counts classify_count_kernel wrote into role_cnt (phase A -> phase C)
   uint32_t *h_pinned = nullptr;                   // plan steps: the two count matrices
   std::vector<uint64_t> last_counts;              // pbf_dist_advance_host: particles every rank returned last time
   // feedback for the load balance: lambda-pass time of this rank on the step before a plan step
@@ -182,7 +183,7 @@ struct pbf_dist_state {
     up_pos.release(); up_vel.release(); up_col.release(); up_ids.release();
     d_splits.release(); d_row.release(); d_hist.release(); d_scratch.release();
     mask.release(); send_idx.release(); leave_idx.release(); blk_cnt.release(); v2.release(); role.release();
-    role_cnt.release(); ring1_idx.release(); bnd_idx.release(); int_idx.release(); pstar1.release();
+    role_cnt.release(); ring1_idx.release(); bnd_idx.release(); pstar1.release();
     if (dyn) cudaFree(dyn);
     if (h_dyn) cudaFreeHost(h_dyn);
     if (bar_word) cudaFree(bar_word);
@@ -215,11 +216,14 @@ __device__ __forceinline__ int owner_of(const uint32_t *splits, int world, uint3
 }
 
 // Destination of every held particle after predict_key: mask[i] = 1 << owner when the owner is another rank, else 0
-// (the same mask format as the ghost lists, so ghost_count_kernel / ghost_scatter_kernel build the leave lists);
-// *n_outside counts particles predicted outside the grid (key >= G), which the last rank owns.
-__global__ void classify_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_dev,
-                                const uint32_t *__restrict__ splits_g, int rank, int world, uint32_t G,
-                                uint32_t *__restrict__ mask, uint32_t *__restrict__ n_outside) {
+// (the same mask format as the ghost lists, so ghost_scatter_kernel builds the leave lists), and in the same pass the
+// per-tile counts the two compactions of the migration need: cnt[d * nblk + blk] = particles of the tile leaving for rank d
+// (totals into row[d]) and kept[blk] = particles of the tile that stay.  *n_outside counts particles predicted outside the
+// grid (key >= G), which the last rank owns.
+__global__ void classify_count_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_dev,
+                                      const uint32_t *__restrict__ splits_g, int rank, int world, uint32_t G, uint32_t nblk,
+                                      uint32_t *__restrict__ mask, uint32_t *__restrict__ cnt, uint32_t *__restrict__ kept,
+                                      uint32_t *__restrict__ row, uint32_t *__restrict__ n_outside) {
   __shared__ uint32_t splits[kMaxWorld + 1];
   if (threadIdx.x <= (unsigned)world) splits[threadIdx.x] = splits_g[threadIdx.x];
   __syncthreads();
@@ -227,9 +231,20 @@ __global__ void classify_kernel(const uint32_t *__restrict__ keys, const uint32_
   const uint32_t i = blockIdx.x * kBlk + threadIdx.x;
   const uint32_t key = i < n ? __ldg(keys + i) : 0u;
   const int o = owner_of(splits, world, key);
-  if (i < n) mask[i] = o == rank ? 0u : 1u << o;
+  const uint32_t m = (i < n && o != rank) ? 1u << o : 0u;
+  if (i < n) mask[i] = m;
   const int outside = __syncthreads_count(i < n && key >= G);
   if (threadIdx.x == 0 && outside) atomicAdd(n_outside, (uint32_t)outside);
+  const int stay = __syncthreads_count(i < n && m == 0u);
+  if (threadIdx.x == 0) kept[blockIdx.x] = (uint32_t)stay;
+  const int leaving = __syncthreads_count(m != 0u);  // block-uniform: most tiles lose nobody
+  for (int d = 0; d < world; ++d) {
+    const int c = leaving ? __syncthreads_count((m >> d) & 1u) : 0;
+    if (threadIdx.x == 0) {
+      cnt[(uint32_t)d * nblk + blockIdx.x] = (uint32_t)c;
+      if (c) atomicAdd(row + d, (uint32_t)c);
+    }
+  }
 }
 
 // Ghost destinations of every owned particle: bit d of mask[i] = rank d needs particle i as a ghost, i.e. owns a cell
@@ -325,11 +340,12 @@ __global__ void ghost_scatter_kernel(const uint32_t *__restrict__ mask, const ui
 }
 
 // This rank's count row -> row `me` of a count matrix in EVERY rank's arena (peer stores).
+// `held` (migration row only): the number of particles this rank holds, which travels as the row's last word.
 __global__ void push_row_kernel(PeerTable peers, size_t rows_off, int me, int world, uint32_t row_words,
-                                const uint32_t *__restrict__ row) {
+                                const uint32_t *__restrict__ row, const uint32_t *__restrict__ held) {
   for (uint32_t t = threadIdx.x; t < (uint32_t)world * row_words; t += blockDim.x) {
     const uint32_t w = t % row_words, q = t / row_words;
-    arena_ptr<uint32_t>(peers.base[q], rows_off)[(size_t)me * row_words + w] = row[w];
+    arena_ptr<uint32_t>(peers.base[q], rows_off)[(size_t)me * row_words + w] = (held && w == (uint32_t)world + 1u) ? __ldg(held) : row[w];
   }
 }
 
@@ -399,41 +415,29 @@ __global__ void push_migrants_kernel(const SlabDyn *__restrict__ dyn, PeerTable 
 }
 
 // Merge input of phase C: keys k2 = [arrivals from lower ranks (stored by their senders) | kept, in input order |
-// arrivals from higher ranks (stored by their senders)], values v2 = index of each entry in the input arrays.
-__global__ void merge_prepare_kernel(const SlabDyn *__restrict__ dyn, const uint32_t *__restrict__ kept_idx,
-                                     const uint32_t *__restrict__ key_in, uint32_t *__restrict__ k2,
-                                     uint32_t *__restrict__ v2) {
-  const uint32_t t = blockIdx.x * kBlk + threadIdx.x;
-  if (t >= dyn->n_own) return;
-  const uint32_t in_lo = dyn->in_lo, n_keep = dyn->n_keep, n_in = dyn->n_in;
-  if (t < in_lo) v2[t] = n_in + t;  // arrivals sit behind the held particles, in source-rank order
-  else if (t < in_lo + n_keep) {
-    const uint32_t s = __ldg(kept_idx + (t - in_lo));
-    v2[t] = s;
-    k2[t] = __ldg(key_in + s);
-  } else v2[t] = n_in + (t - n_keep);
-}
-
-// Stable compaction of the kept particles (mask == 0): per-tile counts, then scatter (the scan between them is
-// exclusive_scan_u32 over the capacity-sized tile array).
-__global__ void kept_count_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ n_dev,
-                                  uint32_t *__restrict__ cnt) {
-  const uint32_t t = blockIdx.x * kBlk + threadIdx.x;
-  const int c = __syncthreads_count(t < __ldg(n_dev) && __ldg(mask + t) == 0u);
-  if (threadIdx.x == 0) cnt[blockIdx.x] = (uint32_t)c;
-}
-__global__ void kept_scatter_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ n_dev,
-                                    const uint32_t *__restrict__ offs, uint32_t *__restrict__ out) {
+// arrivals from higher ranks (stored by their senders)], values v2 = index of each entry in the input arrays.  One
+// kernel: thread t stably compacts held particle t into the kept block (per-tile offsets `offs` = the scanned `kept`
+// counts of classify_count_kernel) and fills the value of merge slot t when that slot belongs to an arrival.
+__global__ void merge_scatter_kernel(const SlabDyn *__restrict__ dyn, const uint32_t *__restrict__ mask,
+                                     const uint32_t *__restrict__ offs, const uint32_t *__restrict__ key_in,
+                                     uint32_t *__restrict__ k2, uint32_t *__restrict__ v2) {
   __shared__ uint32_t wsum[kBlk / 32];
   const uint32_t t = blockIdx.x * kBlk + threadIdx.x;
-  const bool bit = t < __ldg(n_dev) && __ldg(mask + t) == 0u;
+  const uint32_t in_lo = dyn->in_lo, n_keep = dyn->n_keep, n_in = dyn->n_in, n_own = dyn->n_own;
+  if (t < n_own) {  // arrivals sit behind the held particles of the input arrays, in source-rank order
+    if (t < in_lo) v2[t] = n_in + t;
+    else if (t >= in_lo + n_keep) v2[t] = n_in + (t - n_keep);
+  }
+  const bool bit = t < n_in && __ldg(mask + t) == 0u;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned b = __ballot_sync(0xFFFFFFFFu, bit);
   if (lane == 0) wsum[warp] = __popc(b);
   __syncthreads();
-  uint32_t base = __ldg(offs + blockIdx.x);
-  for (unsigned w = 0; w < warp; ++w) base += wsum[w];
-  if (bit) out[base + __popc(b & ((1u << lane) - 1u))] = t;
+  if (!bit) return;
+  uint32_t slot = in_lo + __ldg(offs + blockIdx.x) + __popc(b & ((1u << lane) - 1u));
+  for (unsigned w = 0; w < warp; ++w) slot += wsum[w];
+  v2[slot] = t;
+  k2[slot] = __ldg(key_in + t);
 }
 
 // After barrier 3: the ghost matrix GC (row s, column t = owned particles of s that t holds as ghosts) and the
@@ -552,14 +556,8 @@ __global__ void ghost_fix_kernel(const SlabDyn *__restrict__ dyn, ArenaLayout la
   pstar[i] = p;
 }
 
-__global__ void copy_keys_kernel(const SlabDyn *__restrict__ dyn, const uint32_t *__restrict__ keys_sorted,
-                                 uint32_t *__restrict__ keys_local_own) {
-  const uint32_t i = blockIdx.x * kBlk + threadIdx.x;
-  if (i < dyn->n_own) keys_local_own[i] = __ldg(keys_sorted + i);
-}
-
 // Role of every particle of the local array for the solver passes (static within a step), as per-tile counts for the
-// three compact lists the passes run over:
+// two compact lists the passes run over (the interior pass runs over the owned range in place, skipping the boundary):
 //   ring-1 ghosts   a ghost one of whose 27 cells is ours: lambda is computed here (besides the owned particles)
 //   boundary        owned, and some other rank holds it as a ghost: its delta pass runs first so the halo can leave
 //   interior        owned, nobody else needs it: its delta pass overlaps the halo push
@@ -593,30 +591,29 @@ __global__ void roles_kernel(const uint32_t *__restrict__ keys, const uint32_t *
     }
     role[t] = f;
   }
-  for (uint32_t k = 0; k < 3u; ++k) {
+  for (uint32_t k = 0; k < 2u; ++k) {
     const int c = __syncthreads_count((f >> k) & 1u);
     if (threadIdx.x == 0) cnt[k * nblk + blockIdx.x] = (uint32_t)c;
   }
 }
-// the three lists (absolute indices, ascending) from the scanned tile counts; list k starts at offs[k * nblk]
+// the two lists (absolute indices, ascending) from the scanned tile counts; list k starts at offs[k * nblk]
 __global__ void role_lists_kernel(const uint32_t *__restrict__ role, SlabDyn *__restrict__ dyn, uint32_t nblk,
                                   const uint32_t *__restrict__ offs, const uint32_t *__restrict__ total,
-                                  uint32_t *__restrict__ ring1, uint32_t *__restrict__ bnd, uint32_t *__restrict__ inter,
-                                  uint32_t cap_ring1, uint32_t cap_own) {
+                                  uint32_t *__restrict__ ring1, uint32_t *__restrict__ bnd, uint32_t cap_ring1,
+                                  uint32_t cap_own) {
   __shared__ uint32_t wsum[kBlk / 32];
   const uint32_t t = blockIdx.x * kBlk + threadIdx.x;
   const uint32_t n_local = dyn->n_local;
   if (t == 0) {
     const uint32_t r1 = offs[nblk] - offs[0];
     dyn->n_ring1 = min(r1, cap_ring1);
-    dyn->n_boundary = min(offs[2 * nblk] - offs[nblk], cap_own);
-    dyn->n_interior = min(__ldg(total) - offs[2 * nblk], cap_own);
+    dyn->n_boundary = min(__ldg(total) - offs[nblk], cap_own);
     if (r1 > cap_ring1) atomicOr(&dyn->overflow, 2u);
   }
   if (blockIdx.x * kBlk >= n_local) return;
   const uint32_t f = t < n_local ? __ldg(role + t) : 0u;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t k = 0; k < 3u; ++k) {
+  for (uint32_t k = 0; k < 2u; ++k) {
     const bool bit = (f >> k) & 1u;
     const unsigned b = __ballot_sync(0xFFFFFFFFu, bit);
     if (lane == 0) wsum[warp] = __popc(b);
@@ -624,7 +621,7 @@ __global__ void role_lists_kernel(const uint32_t *__restrict__ role, SlabDyn *__
     uint32_t base = __ldg(offs + k * nblk + blockIdx.x) - __ldg(offs + k * nblk);
     for (unsigned w = 0; w < warp; ++w) base += wsum[w];
     const uint32_t slot = base + __popc(b & ((1u << lane) - 1u));
-    uint32_t *out = k == 0 ? ring1 : (k == 1 ? bnd : inter);
+    uint32_t *out = k == 0 ? ring1 : bnd;
     if (bit && slot < (k == 0 ? cap_ring1 : cap_own)) out[slot] = dyn->first_local + t;
     __syncthreads();
   }
@@ -632,9 +629,6 @@ __global__ void role_lists_kernel(const uint32_t *__restrict__ role, SlabDyn *__
 
 __global__ void set_count_kernel(SlabDyn *__restrict__ dyn, uint32_t n_in) {
   if (threadIdx.x == 0 && blockIdx.x == 0) dyn->n_in = n_in;
-}
-__global__ void row_tail_kernel(uint32_t *__restrict__ row, int W, const uint32_t *__restrict__ n_in) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) row[W + 1] = *n_in;
 }
 // end of a step: the next one starts from this step's owned particles
 __global__ void next_step_kernel(SlabDyn *__restrict__ dyn) {
@@ -724,6 +718,11 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 ArenaLayout make_layout(uint32_t cap_g, uint32_t cap_own, int world) {
   ArenaLayout l;
+  // Capacities are multiples of 256 elements: the owned block starts at element cap_g of every array, and the solver
+  // passes index the neighbour-list rows, pStar and the keys by that position — a warp's 32 consecutive particles must
+  // start on a 128-byte line (an odd cap_g made every coalesced access of the iteration kernels straddle two lines).
+  cap_g = (uint32_t)align_up(cap_g, 256);
+  cap_own = (uint32_t)align_up(cap_own, 256);
   l.cap_g = cap_g; l.cap_own = cap_own; l.cap_local = cap_g + cap_own + cap_g; l.own_off = cap_g;
   l.world = (uint32_t)world; l.row_words = (uint32_t)world + 2u;
   size_t at = 0;
@@ -784,6 +783,8 @@ int build_arenas(std::vector<pbf_ctx *> &L, uint32_t cap_g, uint32_t cap_own, co
       borrow(c->ids[i], fresh + nl.ids[i], nl.cap_local);
     }
     borrow(c->pstar[0], fresh + nl.pstar0, nl.cap_local);
+    // the radix sort's last pass lands in key_a: make that the owned block of the local key array (no copy in phase D)
+    borrow(c->key_a, fresh + nl.keys_local + (size_t)nl.own_off * 4, nl.cap_local - nl.own_off);
     // buffers sized by the capacities, never re-allocated in mid-step (those that may hold live data keep it)
     PBF_CUDA(c, d->pstar1.reserve(nl.cap_local));
     borrow(c->pstar[1], d->pstar1.p, nl.cap_local);
@@ -796,8 +797,7 @@ int build_arenas(std::vector<pbf_ctx *> &L, uint32_t cap_g, uint32_t cap_own, co
     PBF_CUDA(c, d->role.reserve(nl.cap_local));
     PBF_CUDA(c, d->ring1_idx.reserve((size_t)2 * nl.cap_g + 1));
     PBF_CUDA(c, d->bnd_idx.reserve(nl.cap_own + 1));
-    PBF_CUDA(c, d->int_idx.reserve(nl.cap_own + 1));
-    PBF_CUDA(c, d->role_cnt.reserve((size_t)3 * div_up(nl.cap_local, kBlk) + 8));
+    PBF_CUDA(c, d->role_cnt.reserve((size_t)3 * div_up(nl.cap_local, kBlk) + 8, true, c->stream));  // holds the kept counts across a re-grow
     PBF_CUDA(c, c->rho.reserve(nl.cap_local));
   }
   // peer tables
@@ -843,7 +843,7 @@ int build_arenas(std::vector<pbf_ctx *> &L, uint32_t cap_g, uint32_t cap_own, co
   return PBF_OK;
 }
 
-uint32_t headroom(uint64_t n) { return (uint32_t)std::min<uint64_t>(0xFFFF0000ull, n + n / 2 + 4096); }
+uint32_t headroom(uint64_t n) { return (uint32_t)std::min<uint64_t>(0xFFFF0000ull, (n + n / 2 + 4096 + 255) / 256 * 256); }
 
 // ------------------------------------------------------------------------------------------------- host planning
 void plan_splits(const uint64_t *hist, uint32_t n_buckets, uint32_t shift, int world, uint32_t *splits) {
@@ -941,14 +941,11 @@ int phase_a2(pbf_ctx *c) {
   PBF_CUDA(c, cudaSetDevice(c->device));
   PhaseScope ps(c, PBF_PH_HALO);
   PBF_CUDA(c, cudaMemsetAsync(d->d_row.p, 0, (W + 2) * 4, c->stream));
-  const uint32_t nblk = d->cnt_nblk = div_up(l.cap_local - l.own_off, kBlk);
-  classify_kernel<<<nblk, kBlk, 0, c->stream>>>(c->key_in.p, &d->dyn->n_in, d->d_splits.p, d->rank, W, c->sc.G, d->mask.p, d->d_row.p + W);
+  const uint32_t nblk = d->cnt_nblk = d->kept_nblk = div_up(l.cap_local - l.own_off, kBlk);
+  classify_count_kernel<<<nblk, kBlk, 0, c->stream>>>(c->key_in.p, &d->dyn->n_in, d->d_splits.p, d->rank, W, c->sc.G, nblk, d->mask.p,
+                                                      d->blk_cnt.p, d->role_cnt.p, d->d_row.p, d->d_row.p + W);
   PBF_LAUNCH_CHECK(c);
-  ghost_count_kernel<<<nblk, kBlk, 0, c->stream>>>(d->mask.p, &d->dyn->n_in, W, nblk, d->blk_cnt.p, d->d_row.p);
-  PBF_LAUNCH_CHECK(c);
-  row_tail_kernel<<<1, 32, 0, c->stream>>>(d->d_row.p, W, &d->dyn->n_in);
-  PBF_LAUNCH_CHECK(c);
-  push_row_kernel<<<1, 256, 0, c->stream>>>(d->peers, l.rows[0], d->rank, W, l.row_words, d->d_row.p);
+  push_row_kernel<<<1, 256, 0, c->stream>>>(d->peers, l.rows[0], d->rank, W, l.row_words, d->d_row.p, &d->dyn->n_in);
   PBF_LAUNCH_CHECK(c);
   return PBF_OK;
 }
@@ -982,17 +979,14 @@ int phase_c(pbf_ctx *c) {
   const int W = d->world, r = d->rank;
   const ArenaLayout &l = d->lay;
   PBF_CUDA(c, cudaSetDevice(c->device));
-  const uint32_t n_cap = l.cap_local - l.own_off, nblk = div_up(n_cap, kBlk);
+  const uint32_t n_cap = l.cap_local - l.own_off;
+  const uint32_t nblk = d->kept_nblk;  // as counted in phase A (a plan step may have grown the arena since)
   uint32_t *k2 = arena_ptr<uint32_t>(d->arena, l.k2);
   {
     PhaseScope ps(c, PBF_PH_HALO);
-    // kept = mask 0, in input order (leave_idx is free again: the migrants have left)
-    kept_count_kernel<<<nblk, kBlk, 0, c->stream>>>(d->mask.p, &d->dyn->n_in, d->role_cnt.p);
-    PBF_LAUNCH_CHECK(c);
+    // kept = mask 0, in input order: per-tile counts from phase A (role_cnt), scanned here, scattered into the merge input
     PBF_TRY(exclusive_scan_u32(c, d->role_cnt.p, d->role_cnt.p, nblk, nullptr));
-    kept_scatter_kernel<<<nblk, kBlk, 0, c->stream>>>(d->mask.p, &d->dyn->n_in, d->role_cnt.p, d->leave_idx.p);
-    PBF_LAUNCH_CHECK(c);
-    merge_prepare_kernel<<<nblk, kBlk, 0, c->stream>>>(d->dyn, d->leave_idx.p, c->key_in.p, k2, d->v2.p);
+    merge_scatter_kernel<<<nblk, kBlk, 0, c->stream>>>(d->dyn, d->mask.p, d->role_cnt.p, c->key_in.p, k2, d->v2.p);
     PBF_LAUNCH_CHECK(c);
   }
   PBF_TRY(radix_sort_pairs(c, k2, n_cap, d->v2.p, &d->dyn->n_own));
@@ -1004,7 +998,7 @@ int phase_c(pbf_ctx *c) {
     PBF_LAUNCH_CHECK(c);
     ghost_count_kernel<<<oblk, kBlk, 0, c->stream>>>(d->mask.p, &d->dyn->n_own, W, oblk, d->blk_cnt.p, d->d_row.p);
     PBF_LAUNCH_CHECK(c);
-    push_row_kernel<<<1, 256, 0, c->stream>>>(d->peers, l.rows[1], r, W, l.row_words, d->d_row.p);
+    push_row_kernel<<<1, 256, 0, c->stream>>>(d->peers, l.rows[1], r, W, l.row_words, d->d_row.p, nullptr);
     PBF_LAUNCH_CHECK(c);
   }
   return PBF_OK;
@@ -1031,8 +1025,6 @@ int phase_d(pbf_ctx *c) {
                          c->ids[o].p + l.own_off, c->pstar[0].p + l.own_off));
   {
     PhaseScope ps(c, PBF_PH_HALO);
-    copy_keys_kernel<<<div_up(l.cap_own, kBlk), kBlk, 0, c->stream>>>(d->dyn, c->keys_sorted, keys_local + l.own_off);
-    PBF_LAUNCH_CHECK(c);
     if (W > 1) {
       const uint32_t oblk = d->cnt_nblk;  // as counted in phase C
       PBF_TRY(exclusive_scan_u32(c, d->blk_cnt.p, d->blk_cnt.p, (uint64_t)W * oblk, nullptr));
@@ -1069,9 +1061,9 @@ int phase_e(pbf_ctx *c) {
     roles_kernel<<<nblk, kBlk, 0, c->stream>>>(keys_local, d->mask.p, d->dyn, l, c->sc.G, d->splits[d->rank], d->splits[d->rank + 1], nblk,
                                                d->role.p, d->role_cnt.p);
     PBF_LAUNCH_CHECK(c);
-    PBF_TRY(exclusive_scan_u32(c, d->role_cnt.p, d->role_cnt.p, (uint64_t)3 * nblk, c->mc_total_dev + 1));
+    PBF_TRY(exclusive_scan_u32(c, d->role_cnt.p, d->role_cnt.p, (uint64_t)2 * nblk, c->mc_total_dev + 1));
     role_lists_kernel<<<nblk, kBlk, 0, c->stream>>>(d->role.p, d->dyn, nblk, d->role_cnt.p, c->mc_total_dev + 1, d->ring1_idx.p, d->bnd_idx.p,
-                                                    d->int_idx.p, 2u * l.cap_g, l.cap_own);
+                                                    2u * l.cap_g, l.cap_own);
     PBF_LAUNCH_CHECK(c);
   }
   {  // colour diffusion beside the solver iterations (as in the single-device step); group_step joins before finalise
@@ -1287,7 +1279,7 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
       lam.first = l.own_off; lam.count_dev = &d->dyn->n_own; lam.idx = d->ring1_idx.p; lam.n_idx_dev = &d->dyn->n_ring1;
       lam.bound = l.cap_own + 2u * l.cap_g;
       bnd.idx = d->bnd_idx.p; bnd.n_idx_dev = &d->dyn->n_boundary; bnd.bound = l.cap_own;
-      inter.idx = d->int_idx.p; inter.n_idx_dev = &d->dyn->n_interior; inter.bound = l.cap_own;
+      inter.first = l.own_off; inter.count_dev = &d->dyn->n_own; inter.skip = d->mask.p; inter.bound = l.cap_own;  // mask != 0: boundary
       if (measure) PBF_CUDA(c, cudaEventRecord(d->ev_lam[2 * it], c->stream));
       PBF_TRY(solver_lambda(c, lam, c->pstar[0].p, c->pstar[1].p, rho));
       if (measure) PBF_CUDA(c, cudaEventRecord(d->ev_lam[2 * it + 1], c->stream));
@@ -1420,6 +1412,7 @@ void dist_release(pbf_ctx *ctx) {
       if (b->borrowed) b->release();
     if (ctx->ids[i].borrowed) ctx->ids[i].release();
   }
+  if (ctx->key_a.borrowed) ctx->key_a.release();
   if (d->comm && g_nccl.handle) g_nccl.CommDestroy(d->comm);
   d->release();
   delete d;

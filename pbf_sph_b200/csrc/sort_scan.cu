@@ -88,32 +88,46 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_apply_kernel(const uin
   if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
 }
 
-// Up to 8 tiles in ONE launch: a single block walks the tiles with a running carry.  The slab path scans a few
-// thousand per-block counters several times per step, right after host read-backs, where every launch is latency.
-constexpr uint64_t kScanSmall = 8ull * kScanTile;  // beyond that the serial walk loses to three parallel launches
-__global__ void __launch_bounds__(kScanThreads) scan_small_kernel(const uint32_t *in, uint64_t n, uint32_t *out,
-                                                                  uint32_t *total_out) {
-  uint32_t carry = 0;
-  for (uint64_t tile = 0; tile * kScanTile < n; ++tile) {
-    const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
-    uint32_t s = 0;
+// Up to 128 K entries in ONE launch by ONE block of 1 024 threads: thread t owns the contiguous slice [t*m, (t+1)*m), sums
+// it (all loads independent: one memory latency), the block scans the 1 024 sums, and the thread writes its slice's running
+// prefix (second read from L1).  The slab path scans a few thousand to a few ten thousand per-tile counters several times
+// per step between dependent kernels, where what counts is latency: the previous form walked 2 048-entry tiles serially
+// with a carry (18 us for 16 K entries); this one takes about the latency of two dependent loads and one block scan.
+// `out` may alias `in` (a thread reads and writes only its own slice).
+constexpr int kScanWide = 1024;
+constexpr uint64_t kScanSmall = 128ull * 1024;
+__global__ void __launch_bounds__(kScanWide) scan_one_block_kernel(const uint32_t *in, uint32_t n, uint32_t *out,
+                                                                   uint32_t *total_out) {
+  __shared__ uint32_t warp_sums[kScanWide / 32];
+  const uint32_t m = (n + kScanWide - 1) / kScanWide;
+  const uint32_t lo = min(n, threadIdx.x * m), hi = min(n, lo + m);
+  uint32_t s = 0;
+  uint32_t i = lo;
+  for (; i + 8 <= hi; i += 8) {
+    uint32_t v[8];
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-      v[k] = (base + k < n) ? in[base + k] : 0u;
-      s += v[k];
-    }
-    uint32_t total;
-    uint32_t run = block_excl_scan(s, &total) + carry;
+    for (int k = 0; k < 8; ++k) v[k] = in[i + k];
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-      if (base + k < n) out[base + k] = run;
-      run += v[k];
-    }
-    carry += total;
-    __syncthreads();  // block_excl_scan's shared scratch is reused by the next tile
+    for (int k = 0; k < 8; ++k) s += v[k];
   }
-  if (total_out && threadIdx.x == 0) *total_out = carry;
+  for (; i < hi; ++i) s += in[i];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t incl = warp_incl_scan(s);
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = warp_sums[lane];
+    const uint32_t wi = warp_incl_scan(w);
+    warp_sums[lane] = wi - w;
+    if (lane == 31 && total_out) *total_out = wi;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[warp] + incl - s;
+  for (i = lo; i < hi; ++i) {
+    const uint32_t v = in[i];
+    out[i] = run;
+    run += v;
+  }
 }
 
 // ======================================= radix sort ============================================================
@@ -253,7 +267,7 @@ int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t
     return PBF_OK;
   }
   if (n <= kScanSmall) {
-    scan_small_kernel<<<1, kScanThreads, 0, ctx->stream>>>(in, n, out, total_out_dev);
+    scan_one_block_kernel<<<1, kScanWide, 0, ctx->stream>>>(in, (uint32_t)n, out, total_out_dev);
     PBF_LAUNCH_CHECK(ctx);
     return PBF_OK;
   }

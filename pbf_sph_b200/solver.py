@@ -58,6 +58,23 @@ class Solver:
         """Parity tests only: depth of the per-iteration neighbour list (192 by default, 96 the other compiled depth)."""
         self._ck(self._L.pbf_debug_set_list_capacity(self._ctx, hits))
 
+    def debug_scan(self, values: np.ndarray):
+        """Parity tests only: the device exclusive prefix sum on a host u32 array -> (prefix, total)."""
+        v = np.ascontiguousarray(values, np.uint32)
+        out = np.empty_like(v)
+        total = C.c_uint32(0)
+        self._ck(self._L.pbf_debug_scan_u32(self._ctx, v.ctypes.data_as(C.c_void_p), len(v), out.ctypes.data_as(C.c_void_p),
+                                            C.byref(total)))
+        return out, int(total.value)
+
+    def debug_sort_pairs(self, keys: np.ndarray):
+        """Parity tests only: the device radix sort of (key, index) pairs -> (sorted keys, stable permutation)."""
+        k = np.ascontiguousarray(keys, np.uint32)
+        ko, po = np.empty_like(k), np.empty_like(k)
+        self._ck(self._L.pbf_debug_sort_pairs(self._ctx, k.ctypes.data_as(C.c_void_p), len(k), ko.ctypes.data_as(C.c_void_p),
+                                              po.ctypes.data_as(C.c_void_p)))
+        return ko, po
+
     def set_stream(self, cuda_stream: int) -> None:
         self._ck(self._L.pbf_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 
