@@ -37,6 +37,7 @@
 #include <nccl.h>  // types and prototypes only; the symbols are resolved with dlsym
 
 #include <algorithm>
+#include <cstdio>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -104,7 +105,9 @@ struct SlabDyn {
   uint32_t n_send;       // owned particles other ranks hold as ghosts, counted once per destination
   uint32_t n_ring1, n_boundary;
   uint32_t any_outside;  // some particle (on any rank) is predicted outside the grid (key >= G)
-  uint32_t overflow;     // bit 0: held / owned particles, bit 1: ghost slots, bit 2: send lists — a capacity was exceeded
+  uint32_t overflow;     // bit 0: held / owned particles, bit 1: ghost slots, bit 2: send lists — a capacity was exceeded; bit 3: barrier timeout
+  uint32_t want[4];      // the UNCLAMPED needs of this rank on this step: ghosts below, ghosts above, send-list entries, held + arrivals
+  uint32_t hot;          // some rank of the group fills a capacity beyond its watermark: re-plan early (the same value on every rank)
   uint32_t own_range[2];    // {own_off, n_own}
   uint32_t local_range[2];  // {first_local, n_local}
   uint32_t mig_send_off[kMaxWorld + 1];  // destination-major leave list: block of destination q
@@ -164,6 +167,13 @@ struct pbf_dist_state {
   DevBuf<float4> pstar1;
   bool diffuse_pending = false;
   uint32_t cnt_nblk = 0;                          // tile stride of blk_cnt as its last count pass wrote it (the arena may grow before the scatter)
+  uint32_t send_plan = 0;                         // send-list entries the last plan sized for (the same on every rank)
+  // early re-plan: the `hot` verdict of every step comes back through a small ring of pinned words, read two steps later
+  // (all ranks read the verdict of the SAME step, so they still agree on which steps are plan steps without talking)
+  static constexpr int kHotRing = 4;
+  uint32_t *h_hot = nullptr;
+  cudaEvent_t ev_step[kHotRing] = {};
+  uint64_t last_plan_step = 0;
   uint32_t kept_nblk = 0;                         // tiles of the kept counts classify_count_kernel wrote into role_cnt (phase A -> phase C)
   uint32_t *h_pinned = nullptr;                   // plan steps: the two count matrices
   std::vector<uint64_t> last_counts;              // pbf_dist_advance_host: particles every rank returned last time
@@ -189,6 +199,9 @@ struct pbf_dist_state {
     if (h_dyn) cudaFreeHost(h_dyn);
     if (bar_word) cudaFree(bar_word);
     if (h_pinned) cudaFreeHost(h_pinned);
+    if (h_hot) cudaFreeHost(h_hot);
+    for (cudaEvent_t e : ev_step)
+      if (e) cudaEventDestroy(e);
     if (comm_stream) cudaStreamDestroy(comm_stream);
     for (cudaEvent_t e : {ev_boundary, ev_halo, ev_bar[0], ev_bar[1]})
       if (e) cudaEventDestroy(e);
@@ -444,7 +457,8 @@ __global__ void merge_scatter_kernel(const SlabDyn *__restrict__ dyn, const uint
 // After barrier 3: the ghost matrix GC (row s, column t = owned particles of s that t holds as ghosts) and the
 // migration matrix (for every rank's n_own) -> local layout and the destinations of this rank's ghost blocks.
 __global__ void plan_ghosts_kernel(const uint32_t *__restrict__ GC, const uint32_t *__restrict__ M, int me, int W,
-                                   uint32_t row_words, ArenaLayout lay, uint32_t send_cap, SlabDyn *__restrict__ dyn) {
+                                   uint32_t row_words, ArenaLayout lay, uint32_t send_cap, uint32_t send_plan,
+                                   SlabDyn *__restrict__ dyn) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   auto own_of = [&](int q) {
     uint32_t n = M[q * row_words + W + 1];
@@ -458,6 +472,20 @@ __global__ void plan_ghosts_kernel(const uint32_t *__restrict__ GC, const uint32
     n_send += GC[me * row_words + q];
     if (q < me) n_glo += GC[q * row_words + me]; else n_ghi += GC[q * row_words + me];
   }
+  dyn->want[0] = n_glo; dyn->want[1] = n_ghi; dyn->want[2] = n_send;
+  // Watermarks, for EVERY rank of the group from the two matrices every rank holds (so all ranks reach the same verdict
+  // without talking): ghosts or send lists beyond 3/4, owned particles beyond 7/8 of the capacity the last plan gave them.
+  uint32_t hot = 0;
+  for (int q = 0; q < W; ++q) {
+    uint64_t lo = 0, hi = 0, snd = 0;
+    for (int t = 0; t < W; ++t) {
+      if (t == q) continue;
+      snd += GC[q * row_words + t];
+      if (t < q) lo += GC[t * row_words + q]; else hi += GC[t * row_words + q];
+    }
+    if (4 * lo > 3ull * lay.cap_g || 4 * hi > 3ull * lay.cap_g || 4 * snd > 3ull * send_plan || 8ull * own_of(q) > 7ull * lay.cap_own) hot = 1;
+  }
+  dyn->hot = hot;
   uint32_t ov = 0;
   if (n_send > send_cap) { n_send = send_cap; ov |= 4u; }
   if (n_glo > lay.cap_g || n_ghi > lay.cap_g || (uint64_t)lay.own_off + dyn->n_own + n_ghi > lay.cap_local) ov |= 2u;
@@ -802,6 +830,15 @@ int build_arenas(std::vector<pbf_ctx *> &L, uint32_t cap_g, uint32_t cap_own, co
       PBF_CUDA(c, cudaMemcpyAsync(fresh + nl.ids[c->cur] + (size_t)nl.own_off * 8, d->arena + ol.ids[c->cur] + (size_t)ol.own_off * 8,
                                   keep * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
+    // the sorted keys of the step in flight live in the owned block of the local key array (key_a is borrowed from the
+    // arena): a re-grow between the sort and the reorder (plan steps, exact ghost counts) must carry them over
+    const bool keys_in_arena = d->arena && c->key_a.borrowed && c->keys_sorted == c->key_a.p;
+    if (keys_in_arena) {
+      const ArenaLayout &ol = d->lay;
+      const size_t n_keys = std::min<size_t>(ol.cap_local - ol.own_off, nl.cap_local - nl.own_off);
+      PBF_CUDA(c, cudaMemcpyAsync(fresh + nl.keys_local + (size_t)nl.own_off * 4, d->arena + ol.keys_local + (size_t)ol.own_off * 4,
+                                  n_keys * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
     PBF_CUDA(c, cudaStreamSynchronize(c->stream));
     d->release_arena();
     d->arena = fresh;
@@ -816,6 +853,7 @@ int build_arenas(std::vector<pbf_ctx *> &L, uint32_t cap_g, uint32_t cap_own, co
     borrow(c->pstar[0], fresh + nl.pstar0, nl.cap_local);
     // the radix sort's last pass lands in key_a: make that the owned block of the local key array (no copy in phase D)
     borrow(c->key_a, fresh + nl.keys_local + (size_t)nl.own_off * 4, nl.cap_local - nl.own_off);
+    if (keys_in_arena) c->keys_sorted = c->key_a.p;
     // buffers sized by the capacities, never re-allocated in mid-step (those that may hold live data keep it)
     PBF_CUDA(c, d->pstar1.reserve(nl.cap_local));
     borrow(c->pstar[1], d->pstar1.p, nl.cap_local);
@@ -1046,7 +1084,7 @@ int phase_d(pbf_ctx *c) {
   {
     PhaseScope ps(c, PBF_PH_HALO);
     plan_ghosts_kernel<<<1, 32, 0, c->stream>>>(arena_ptr<uint32_t>(d->arena, l.rows[1]), arena_ptr<uint32_t>(d->arena, l.rows[0]), r, W,
-                                                l.row_words, l, (uint32_t)d->send_idx.cap, d->dyn);
+                                                l.row_words, l, (uint32_t)d->send_idx.cap, d->send_plan, d->dyn);
     PBF_LAUNCH_CHECK(c);
   }
   c->sc.n = l.cap_own;
@@ -1115,12 +1153,14 @@ int phase_e(pbf_ctx *c) {
 }
 
 // Growth decision of a plan step, the same on every rank (same inputs, same arithmetic).
+// A capacity grows as soon as less than the watermarks of plan_ghosts_kernel would be left free (owned: the need plus a
+// quarter; ghosts: plus two fifths), and then to 1.5 x the need: right after a plan step no rank is `hot`.  0 = no opinion.
 bool need_growth(const ArenaLayout &l, uint64_t want_own, uint64_t want_g, uint32_t &cap_g, uint32_t &cap_own) {
   cap_g = l.cap_g;
   cap_own = l.cap_own;
   bool grow = false;
-  if (want_own > l.cap_own) { cap_own = headroom(want_own); grow = true; }
-  if (want_g > l.cap_g) { cap_g = headroom(want_g); grow = true; }
+  if (want_own && want_own + want_own / 4 > l.cap_own) { cap_own = headroom(want_own); grow = true; }
+  if (want_g && want_g + 2 * want_g / 5 > l.cap_g) { cap_g = headroom(want_g); grow = true; }
   return grow;
 }
 
@@ -1170,7 +1210,18 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
   for (pbf_ctx *c : L) any_fresh |= c->dist->fresh;
   // NCCL ranks agree on "is this a plan step" without talking: uploads are collective by contract and the schedule is a
   // function of the step index.
-  const bool replan = d0->splits.empty() || (d0->replan_every && d0->step_index % d0->replan_every == 0);
+  // ... and of the `hot` verdict of the step two back (identical on every rank; a verdict older than the last plan is stale).
+  bool hot = false;
+  if (d0->step_index >= 2 && d0->step_index - 2 > d0->last_plan_step) {
+    for (pbf_ctx *c : L) {
+      D *d = c->dist;
+      const int slot = (int)((d->step_index - 2) % D::kHotRing);
+      PBF_CUDA(c, cudaSetDevice(c->device));
+      PBF_CUDA(c, cudaEventSynchronize(d->ev_step[slot]));
+      hot |= d->h_hot[slot] != 0u;
+    }
+  }
+  const bool replan = d0->splits.empty() || hot || (d0->replan_every && d0->step_index % d0->replan_every == 0);
   const bool plan = replan || any_fresh || !d0->arena;
   const bool measure = d0->replan_every && (d0->step_index + 1) % d0->replan_every == 0 && p.iteration <= (uint64_t)kMaxTimedIters;
 
@@ -1190,7 +1241,7 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
     uint64_t max_held = 0, total = 0;
     for (uint64_t h : all_held) { max_held = std::max(max_held, h); total += h; }
     const uint64_t want_own = std::max<uint64_t>(max_held, (total + W - 1) / W) + 256;
-    const uint64_t want_g = d0->arena ? d0->lay.cap_g : std::max<uint64_t>(1024, want_own / 3);
+    const uint64_t want_g = d0->arena ? 0 : std::max<uint64_t>(1024, want_own / 3);
     uint32_t cap_g, cap_own;
     if (need_growth(d0->lay, want_own, want_g, cap_g, cap_own) || !d0->arena) {
       std::vector<uint64_t> live(L.size(), 0);
@@ -1207,7 +1258,10 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
   if (replan) {
     PBF_TRY(all_reduce_sum_u32(L, [](pbf_ctx *c) { return c->dist->d_hist.p; }, L[0]->dist->hist_buckets));
     // what every rank measured on the step before: lambda-pass milliseconds against the work the last plan gave it
-    if (!d0->splits.empty() && !d0->last_weights.empty()) {
+    bool shared_device = false;  // ranks that share a GPU time each other's kernels: no feedback from such a group
+    for (size_t a = 0; a < L.size(); ++a)
+      for (size_t b = a + 1; b < L.size(); ++b) shared_device |= L[a]->device == L[b]->device;
+    if (!d0->splits.empty() && !d0->last_weights.empty() && !shared_device) {
       std::vector<uint64_t> mine(L.size()), all;
       for (size_t r = 0; r < L.size(); ++r) mine[r] = (uint64_t)(L[r]->dist->busy_ms * 1e6);
       PBF_TRY(all_gather_host(L, mine, all));
@@ -1222,7 +1276,7 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
         mean /= W;
         for (int r = 0; r < W; ++r) {
           const double prev = d0->rate.size() == (size_t)W ? d0->rate[r] : 1.0;
-          rate[r] = std::min(2.5, std::max(0.4, prev * std::pow(rate[r] / mean, 0.75)));  // damped: regions shift with the splits
+          rate[r] = std::min(1.7, std::max(0.6, prev * std::pow(rate[r] / mean, 0.75)));  // damped: regions shift with the splits
         }
         for (pbf_ctx *c : L) c->dist->rate = rate;
       }
@@ -1249,7 +1303,7 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
       live[r] = M[c->dist->rank * RW + W + 1];
     }
     uint32_t cap_g, cap_own;
-    if (need_growth(d0->lay, want_own + 256, d0->lay.cap_g, cap_g, cap_own)) PBF_TRY(regrow(L, cap_g, cap_own, live, 1, p));
+    if (need_growth(d0->lay, want_own + 256, 0, cap_g, cap_own)) PBF_TRY(regrow(L, cap_g, cap_own, live, 1, p));
   }
   for (pbf_ctx *c : L) PBF_TRY(phase_b(c));
   PBF_TRY(barrier(L, 0));
@@ -1280,12 +1334,13 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
       live[r] = in;
     }
     uint32_t cap_g, cap_own;
-    if (need_growth(d0->lay, d0->lay.cap_own, want_g + 256, cap_g, cap_own)) PBF_TRY(regrow(L, cap_g, cap_own, live, 2, p));
+    if (need_growth(d0->lay, 0, want_g + 256, cap_g, cap_own)) PBF_TRY(regrow(L, cap_g, cap_own, live, 2, p));
     for (pbf_ctx *c : L) {  // send lists: local buffers, every rank sized for the largest list of the group
       PBF_CUDA(c, cudaSetDevice(c->device));
-      if (want_send + 256 > c->dist->send_idx.cap) {
+      if (want_send + 2 * want_send / 5 + 256 > c->dist->send_plan) c->dist->send_plan = headroom(want_send);
+      if (c->dist->send_plan > c->dist->send_idx.cap) {
         PBF_CUDA(c, cudaStreamSynchronize(c->stream));
-        PBF_CUDA(c, c->dist->send_idx.reserve(headroom(want_send)));
+        PBF_CUDA(c, c->dist->send_idx.reserve(c->dist->send_plan));
       }
     }
   }
@@ -1369,6 +1424,12 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
     next_step_kernel<<<1, 32, 0, c->stream>>>(d->dyn);
     PBF_LAUNCH_CHECK(c);
     PBF_CUDA(c, cudaMemcpyAsync(d->h_dyn, d->dyn, sizeof(SlabDyn), cudaMemcpyDeviceToHost, c->stream));
+    {
+      const int slot = (int)(d->step_index % D::kHotRing);
+      PBF_CUDA(c, cudaMemcpyAsync(d->h_hot + slot, &d->dyn->hot, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      PBF_CUDA(c, cudaEventRecord(d->ev_step[slot], c->stream));
+      if (plan) d->last_plan_step = d->step_index;
+    }
     c->have_state = true;
     c->prof.steps++;
     d->step_index++;
@@ -1407,6 +1468,9 @@ int dist_alloc(pbf_ctx *c, int rank, int world) {
   PBF_CUDA(c, cudaMemset(d->dyn, 0, sizeof(SlabDyn)));
   PBF_CUDA(c, cudaHostAlloc(&d->h_dyn, sizeof(SlabDyn), cudaHostAllocDefault));
   std::memset(d->h_dyn, 0, sizeof(SlabDyn));
+  PBF_CUDA(c, cudaHostAlloc(&d->h_hot, D::kHotRing * sizeof(uint32_t), cudaHostAllocDefault));
+  std::memset(d->h_hot, 0, D::kHotRing * sizeof(uint32_t));
+  for (cudaEvent_t &e : d->ev_step) PBF_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   PBF_CUDA(c, cudaMalloc(&d->bar_word, 64));
   PBF_CUDA(c, cudaMemset(d->bar_word, 0, 64));
   PBF_CUDA(c, cudaHostAlloc(&d->h_pinned, ((size_t)2 * (world + 1) * (world + 2) + 64) * 4, cudaHostAllocDefault));
@@ -1436,11 +1500,18 @@ int dist_refresh_counts(pbf_ctx *c) {
   PBF_CUDA(c, cudaSetDevice(c->device));
   PBF_CUDA(c, cudaStreamSynchronize(c->stream));
   if (d->fresh) { c->n = d->n_up; return PBF_OK; }
-  if (d->h_dyn->overflow)
-    return fail(c, PBF_ERR_CAPACITY, "slab arena",
-                d->h_dyn->overflow & 8u   ? "a peer rank did not reach a barrier within 4 s (it failed or fell behind by a plan step)"
-                : d->h_dyn->overflow & 1u ? "more particles arrived between two plan steps than the arena holds (lower pbf_dist_set_replan)"
-                                          : "more ghosts between two plan steps than the arena holds (lower pbf_dist_set_replan)");
+  if (d->h_dyn->overflow) {
+    const SlabDyn &h = *d->h_dyn;
+    char msg[512];
+    std::snprintf(msg, sizeof msg,
+                  "%s (rank %d, bits 0x%x: ghosts below/above %u/%u of %u, send list %u of %zu, owned %u of %u, ring-1 %u); "
+                  "a capacity set by the last plan step was exceeded",
+                  h.overflow & 8u   ? "a peer rank did not reach a barrier within 4 s"
+                  : h.overflow & 1u ? "more particles arrived between two plan steps than the arena holds"
+                                    : "more ghosts between two plan steps than the arena holds",
+                  d->rank, h.overflow, h.want[0], h.want[1], d->lay.cap_g, h.want[2], d->send_idx.cap, h.n_own, d->lay.cap_own, h.n_ring1);
+    return fail(c, PBF_ERR_CAPACITY, "slab arena", msg);
+  }
   c->n = d->h_dyn->n_own;
   return PBF_OK;
 }
