@@ -463,10 +463,13 @@ def run_single(args):
     secondary = None
     if not args.no_secondary and args.workload in ("auto", "dam-1m"):
         # BASELINE.json configs[3] (surface every step), configs[2] on one GPU, and configs[4]'s first point (8 M, 8 iterations)
-        secondary = secondary_single(torch, s, stream, args, [("dam-1m-mc", [4]), ("dam-8m", [4, 8])])
-        base = ms_total / args.steps * 1e3 / n
-        for e in secondary:
-            e["us_per_particle_step_vs_dam_1m"] = e["us_per_particle_step"] / base if e["solver_iterations"] == iters else None
+        try:  # a failure here is reported in `secondary`, it never takes the primary line down with it
+            secondary = secondary_single(torch, s, stream, args, [("dam-1m-mc", [4]), ("dam-8m", [4, 8])])
+            base = ms_total / args.steps * 1e3 / n
+            for e in secondary:
+                e["us_per_particle_step_vs_dam_1m"] = e["us_per_particle_step"] / base if e["solver_iterations"] == iters else None
+        except Exception as e:  # noqa: BLE001
+            secondary = [{"error": repr(e)}]
     s.close()
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,

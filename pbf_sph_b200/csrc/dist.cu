@@ -678,7 +678,8 @@ __global__ void flag_barrier_kernel(PeerTable peers, size_t flags_off, int me, i
     const uint32_t *mine = arena_ptr<uint32_t>(peers.base[me], flags_off) + q;
     unsigned long long t0 = 0, now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
+    const bool dead = (*(volatile uint32_t *)&dyn->overflow & 8u) != 0u;  // a peer already failed to arrive: never wait again
+    for (; !dead;) {
       uint32_t v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int32_t)(v - epoch) >= 0) break;

@@ -34,8 +34,22 @@ namespace {
 #ifndef PBF_NL_BLOCK
 #define PBF_NL_BLOCK 256
 #endif
-constexpr int kBlock = PBF_NL_BLOCK;  // lambda pass, launches below kLargeLaunch particles
+constexpr int kBlock = PBF_NL_BLOCK;  // lambda pass
 constexpr int kBlockD = 128;          // delta pass (larger blocks measured slower at every size)
+// Layout of the hit list: particles in chunks of kChunk; inside a chunk hit k of particle a lives at
+//   nl[(a / kChunk) * kChunk * (cap + 1) + k * kChunk + a % kChunk]
+// so the 32 lanes of a warp still write / read one 128-byte line per row, but the rows of a particle are kChunk * 4 bytes
+// apart WHATEVER the particle count.  (With rows n * 4 bytes apart the passes slowed down as n grew — the same 1 M particles
+// with rows 32 MB apart, as in an 8 M-particle list: lambda 1.25 -> 1.59 ms per step; profiles/r02c_list_layout.txt.)
+#ifndef PBF_NL_CHUNK_LOG2
+#define PBF_NL_CHUNK_LOG2 15
+#endif
+constexpr uint32_t kChunkLog2 = PBF_NL_CHUNK_LOG2;
+constexpr uint32_t kChunk = 1u << kChunkLog2;
+__device__ __forceinline__ uint32_t list_base(uint32_t a, uint32_t chunk_words) {
+  return (a >> kChunkLog2) * chunk_words + (a & (kChunk - 1u));
+}
+
 #ifndef PBF_NL_ST
 #define PBF_NL_ST ".cs"
 #endif
@@ -81,11 +95,11 @@ __device__ __forceinline__ void store_if(uint32_t *p, uint32_t v, bool pred) {
 // The append of the search loop: store the candidate's index at the particle's next free slot and advance the slot,
 // both under the hit predicate (@p STG + @p IADD: two instructions, where `slot += hit ? stride : 0` costs a select
 // and an add on top of the store).
-__device__ __forceinline__ void append_if(uint32_t *nl, uint32_t &slot, uint32_t v, uint32_t stride, bool pred) {
+__device__ __forceinline__ void append_if(uint32_t *nl, uint32_t &slot, uint32_t v, bool pred) {
   asm volatile(
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global" PBF_NL_ST ".b32 [%1], %2;\n\t@q add.u32 %0, %0, %4;\n\t}"
       : "+r"(slot)
-      : "l"(nl + slot), "r"(v), "r"((uint32_t)pred), "r"(stride)
+      : "l"(nl + slot), "r"(v), "r"((uint32_t)pred), "n"(kChunk)
       : "memory");
 }
 
@@ -95,13 +109,13 @@ __device__ __forceinline__ void append_if(uint32_t *nl, uint32_t &slot, uint32_t
 // pass, whose search loop needs the registers (56 -> 9 blocks per SM).
 template <int kW, bool kSameKernel, typename Acc>
 __device__ __forceinline__ void sum_over_hits(Acc &acc, const StepConst &c, const float4 pa, const float4 *__restrict__ pstar,
-                                              const uint32_t *row, uint32_t stride, uint32_t k, uint32_t self) {
+                                              const uint32_t *row, uint32_t k, uint32_t self) {
   uint32_t i = 0;
-  for (; i + kW <= k; i += kW, row += kW * stride) {
+  for (; i + kW <= k; i += kW, row += kW * kChunk) {
     uint32_t b[kW];
     float4 q[kW];
 #pragma unroll
-    for (int m = 0; m < kW; ++m) b[m] = ld_list(row + m * stride);
+    for (int m = 0; m < kW; ++m) b[m] = ld_list(row + m * kChunk);
 #pragma unroll
     for (int m = 0; m < kW; ++m) q[m] = ldg4(pstar + b[m]);
 #pragma unroll
@@ -113,7 +127,7 @@ __device__ __forceinline__ void sum_over_hits(Acc &acc, const StepConst &c, cons
     float4 q[kW - 1];
 #pragma unroll
     for (int m = 0; m < kW - 1; ++m)
-      b[m] = (uint32_t)m < left ? ld_list(row + m * stride) : self;
+      b[m] = (uint32_t)m < left ? ld_list(row + m * kChunk) : self;
 #pragma unroll
     for (int m = 0; m < kW - 1; ++m) q[m] = ldg4(pstar + b[m]);
 #pragma unroll
@@ -148,7 +162,7 @@ template <bool kStrict, int kCap>
 __device__ __forceinline__ void lambda_particle(const StepConst &c, const uint32_t a, const uint32_t *__restrict__ keys,
                                                 const uint32_t *__restrict__ table, const float4 *__restrict__ pos_mass,
                                                 const float4 *__restrict__ pstar_in, float4 *__restrict__ pstar_out,
-                                                float *__restrict__ rho_out, uint32_t *nl, uint32_t stride, uint32_t inv_stride,
+                                                float *__restrict__ rho_out, uint32_t *nl, uint32_t chunk_words,
                                                 uint32_t *__restrict__ n_hits) {
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t key = __ldg(keys + a);
@@ -166,28 +180,28 @@ __device__ __forceinline__ void lambda_particle(const StepConst &c, const uint32
     const int iz = r / 3, iy = r - 3 * iz;
     return (iz == 0 ? zm : (iz == 1 ? z0 : zp)) | (iy == 0 ? ym : (iy == 1 ? y0 : yp));
   };
-  uint32_t slot = a;  // element index of the next free entry: hit k lives at nl[k * stride + a]
+  const uint32_t base = list_base(a, chunk_words);
+  uint32_t slot = base;  // element index of the next free entry: hit k lives at nl[base + k * kChunk]
   uint32_t over = 0;  // hits that did not fit
   auto scan_run = [&](uint32_t s, uint32_t e) {
-    // hits so far, exactly: (slot - a) is a small multiple of stride, inv_stride = ceil(2^32 / stride)
-    uint32_t k = __umulhi(slot - a, inv_stride);
+    uint32_t k = (slot - base) >> kChunkLog2;  // hits so far
     if (k + (e - s) <= (uint32_t)kCap) {  // cannot overflow: no per-candidate capacity test, no hit counter
       // Whole batches of four, then ONE masked batch for the 1-3 left over: its gathers go out together (indices
       // clamped into the run), where a scalar remainder loop waits out one gather latency per candidate.
       uint32_t b = s;
       for (; b + 4u <= e; b += 4u) {
         const float4 q0 = ldg4s(pstar_in + b), q1 = ldg4s(pstar_in + b + 1), q2 = ldg4s(pstar_in + b + 2), q3 = ldg4s(pstar_in + b + 3);
-        append_if(nl, slot, b, stride, LambdaAcc<kStrict>::test(c, pa, q0));
-        append_if(nl, slot, b + 1u, stride, LambdaAcc<kStrict>::test(c, pa, q1));
-        append_if(nl, slot, b + 2u, stride, LambdaAcc<kStrict>::test(c, pa, q2));
-        append_if(nl, slot, b + 3u, stride, LambdaAcc<kStrict>::test(c, pa, q3));
+        append_if(nl, slot, b, LambdaAcc<kStrict>::test(c, pa, q0));
+        append_if(nl, slot, b + 1u, LambdaAcc<kStrict>::test(c, pa, q1));
+        append_if(nl, slot, b + 2u, LambdaAcc<kStrict>::test(c, pa, q2));
+        append_if(nl, slot, b + 3u, LambdaAcc<kStrict>::test(c, pa, q3));
       }
       if (b < e) {
         const uint32_t last = e - 1u;
         const float4 q0 = ldg4s(pstar_in + b), q1 = ldg4s(pstar_in + min(b + 1u, last)), q2 = ldg4s(pstar_in + min(b + 2u, last));
-        append_if(nl, slot, b, stride, LambdaAcc<kStrict>::test(c, pa, q0));
-        append_if(nl, slot, b + 1u, stride, b + 1u < e && LambdaAcc<kStrict>::test(c, pa, q1));
-        append_if(nl, slot, b + 2u, stride, b + 2u < e && LambdaAcc<kStrict>::test(c, pa, q2));
+        append_if(nl, slot, b, LambdaAcc<kStrict>::test(c, pa, q0));
+        append_if(nl, slot, b + 1u, b + 1u < e && LambdaAcc<kStrict>::test(c, pa, q1));
+        append_if(nl, slot, b + 2u, b + 2u < e && LambdaAcc<kStrict>::test(c, pa, q2));
       }
     } else {
 #pragma unroll 1
@@ -195,7 +209,7 @@ __device__ __forceinline__ void lambda_particle(const StepConst &c, const uint32
         const bool hit = LambdaAcc<kStrict>::test(c, pa, ldg4s(pstar_in + b));
         const bool fits = hit && k < (uint32_t)kCap;
         store_if(nl + slot, b, fits);
-        slot += fits ? stride : 0u;
+        slot += fits ? kChunk : 0u;
         k += fits ? 1u : 0u;
         over += (hit && !fits) ? 1u : 0u;
       }
@@ -210,7 +224,7 @@ __device__ __forceinline__ void lambda_particle(const StepConst &c, const uint32
     scan_run(x_even ? cur.ss : cur.ps, x_even ? cur.se : cur.pe);
     scan_run(x_even ? cur.ps : cur.ss, x_even ? cur.pe : cur.se);
   }
-  const uint32_t k = __umulhi(slot - a, inv_stride) + over;
+  const uint32_t k = ((slot - base) >> kChunkLog2) + over;
   n_hits[a] = k;
 
   // ---- phase 2: the sums over the hits
@@ -218,7 +232,7 @@ __device__ __forceinline__ void lambda_particle(const StepConst &c, const uint32
   acc.init();
   acc.set_mass(mass);
   if (k <= (uint32_t)kCap) {
-    sum_over_hits<4, true>(acc, c, pa, pstar_in, nl + a, stride, k, a);
+    sum_over_hits<4, true>(acc, c, pa, pstar_in, nl + base, k, a);
   } else {
     for_each_candidate(key, c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
@@ -231,32 +245,29 @@ __device__ __forceinline__ void lambda_particle(const StepConst &c, const uint32
 #define PBF_LAMBDA_ARGS                                                                                                  \
   const uint32_t *__restrict__ keys, const uint32_t *__restrict__ table, const float4 *__restrict__ pos_mass,            \
       const float4 *__restrict__ pstar_in, float4 *__restrict__ pstar_out, float *__restrict__ rho_out, uint32_t *nl,    \
-      uint32_t stride, uint32_t inv_stride, uint32_t *__restrict__ n_hits
+      uint32_t chunk_words, uint32_t *__restrict__ n_hits
 
-// One thread per particle, kB threads per block.  The block size sets how well the warps of an SM share their gathers in
-// L1: the hardware deals consecutive blocks to different SMs, so with 128-thread blocks the nine blocks of an SM work on
-// nine unrelated neighbourhoods, while the 32 warps of a 1 024-thread block sweep 1 024 consecutive particles (a compact
-// Morton block of ~160 cells) in step.  While the arrays fit the L2 an L1 miss is cheap and small blocks win (no idle
-// tail inside a block, finer waves); from ~3 M particles on (16 B x n of positions beyond what the L2 keeps beside the
-// list traffic) the extra misses go to DRAM and the large block is 17 % faster (profiles/r02b_block_size.txt).
-template <bool kStrict, int kCap, int kB>
-__global__ void __launch_bounds__(kB, 9 * 128 / kB < 1 ? 1 : 9 * 128 / kB) lambda_list_kernel(StepConst c, Sel sel, PBF_LAMBDA_ARGS) {
+// One thread per particle, 256 per block.  (With the list rows n * 4 bytes apart, 1 024-thread blocks were 17 % faster from
+// ~3 M particles on and were shipped for a few hours; with the chunked list the 256-thread block wins at every size again:
+// dam-8m lambda 13.99 ms per step originally, 11.5 with 1 024-thread blocks, 9.75 now.  profiles/r02b_block_size.txt)
+template <bool kStrict, int kCap>
+__global__ void __launch_bounds__(kBlock, 4) lambda_list_kernel(StepConst c, Sel sel, PBF_LAMBDA_ARGS) {
   uint32_t a;
-  if (!sel_particle(sel, blockIdx.x * kB + threadIdx.x, a)) return;
-  lambda_particle<kStrict, kCap>(c, a, keys, table, pos_mass, pstar_in, pstar_out, rho_out, nl, stride, inv_stride, n_hits);
+  if (!sel_particle(sel, blockIdx.x * kBlock + threadIdx.x, a)) return;
+  lambda_particle<kStrict, kCap>(c, a, keys, table, pos_mass, pstar_in, pstar_out, rho_out, nl, chunk_words, n_hits);
 }
 
 template <bool kStrict, int kCap>
 __device__ __forceinline__ void delta_particle(const StepConst &c, const uint32_t a, const uint32_t *__restrict__ keys,
                                                const uint32_t *__restrict__ table, const float4 *__restrict__ pstar_in,
-                                               float4 *__restrict__ pstar_out, const uint32_t *__restrict__ nl, uint32_t stride,
+                                               float4 *__restrict__ pstar_out, const uint32_t *__restrict__ nl, uint32_t chunk_words,
                                                const uint32_t *__restrict__ n_hits) {
   const float4 pa = ldg4(pstar_in + a);
   const uint32_t k = __ldg(n_hits + a);
   DeltaAcc<kStrict> acc;
   acc.init();
   if (k <= (uint32_t)kCap) {
-    sum_over_hits<8, false>(acc, c, pa, pstar_in, nl + a, stride, k, a);  // add_in skips the particle itself (r < EPSILON)
+    sum_over_hits<8, false>(acc, c, pa, pstar_in, nl + list_base(a, chunk_words), k, a);  // add_in skips the particle itself (r < EPSILON)
   } else {
     for_each_candidate(__ldg(keys + a), c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
@@ -265,39 +276,30 @@ __device__ __forceinline__ void delta_particle(const StepConst &c, const uint32_
 
 #define PBF_DELTA_ARGS                                                                                                   \
   const uint32_t *__restrict__ keys, const uint32_t *__restrict__ table, const float4 *__restrict__ pstar_in,            \
-      float4 *__restrict__ pstar_out, const uint32_t *__restrict__ nl, uint32_t stride, const uint32_t *__restrict__ n_hits
+      float4 *__restrict__ pstar_out, const uint32_t *__restrict__ nl, uint32_t chunk_words, const uint32_t *__restrict__ n_hits
 
 template <bool kStrict, int kCap>
 __global__ void __launch_bounds__(kBlockD, 8) delta_list_kernel(StepConst c, Sel sel, PBF_DELTA_ARGS) {
   uint32_t a;
   if (!sel_particle(sel, blockIdx.x * kBlockD + threadIdx.x, a)) return;
-  delta_particle<kStrict, kCap>(c, a, keys, table, pstar_in, pstar_out, nl, stride, n_hits);
+  delta_particle<kStrict, kCap>(c, a, keys, table, pstar_in, pstar_out, nl, chunk_words, n_hits);
 }
-
-// particles per launch from which the 1 024-thread block pays (see lambda_list_kernel)
-constexpr uint32_t kLargeLaunch = 3000000u;
 
 template <bool kStrict, int kCap> int launch_lambda_mode(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted,
                                                          const uint32_t *table, const float4 *pos_mass, const float4 *pstar_in,
-                                                         float4 *pstar_out, float *rho_out, uint32_t stride) {
-  uint32_t *nl4 = ctx->nl.p;
-  const uint32_t inv_stride = (uint32_t)(((1ull << 32) + stride - 1) / stride);
-  if (sel.bound >= kLargeLaunch)
-    lambda_list_kernel<kStrict, kCap, 1024><<<div_up(sel.bound, 1024u), 1024, 0, ctx->stream>>>(
-        ctx->sc, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, inv_stride, ctx->nl_count.p);
-  else
-    lambda_list_kernel<kStrict, kCap, kBlock><<<div_up(sel.bound, (uint32_t)kBlock), kBlock, 0, ctx->stream>>>(
-        ctx->sc, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, nl4, stride, inv_stride, ctx->nl_count.p);
+                                                         float4 *pstar_out, float *rho_out, uint32_t chunk_words) {
+  lambda_list_kernel<kStrict, kCap><<<div_up(sel.bound, (uint32_t)kBlock), kBlock, 0, ctx->stream>>>(
+      ctx->sc, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, ctx->nl.p, chunk_words, ctx->nl_count.p);
   PBF_LAUNCH_CHECK(ctx);
   return PBF_OK;
 }
 
 template <int kCap> int launch_lambda_cap(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,
                                           const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out,
-                                          uint32_t stride) {
+                                          uint32_t chunk_words) {
   if (ctx->flags & PBF_FLAG_STRICT_FP)
-    return launch_lambda_mode<true, kCap>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride);
-  return launch_lambda_mode<false, kCap>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride);
+    return launch_lambda_mode<true, kCap>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, chunk_words);
+  return launch_lambda_mode<false, kCap>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, chunk_words);
 }
 
 template <bool kStrict, int kCap> int launch_delta_mode(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted,
@@ -322,22 +324,23 @@ int launch_lambda_list(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted
                        const float4 *pos_mass, const float4 *pstar_in, float4 *pstar_out, float *rho_out) {
   if (sel.bound == 0) return PBF_OK;
   const uint32_t n = ctx->sc.n;
-  const uint32_t stride = (n + 31u) & ~31u;  // rows start on 128-byte boundaries
+  const uint32_t n_chunks = div_up(n, kChunk);
   // Rows cost address space, not bandwidth (a row is touched only by particles with that many hits), so the search keeps
   // up to kListWide hits: while a dam break splashes, particles clamped onto the walls pile up (dam-1m after 30 steps:
   // 431 particles with 97..229 neighbours) and every one that overflows drags its block through the one-pass fallback
   // in both passes.  The wide list needs n < 2^32 / 193 = 22 M particles per device; above that the list is kListMax deep.
   uint32_t cap = (uint32_t)ctx->list_cap;
-  if (cap == kListWide && (uint64_t)stride * (kListWide + 1) >= (1ull << 32)) cap = kListMax;
-  if ((uint64_t)stride * (cap + 1) >= (1ull << 32))
+  if (cap == kListWide && (uint64_t)n_chunks * kChunk * (kListWide + 1) >= (1ull << 32)) cap = kListMax;
+  if ((uint64_t)n_chunks * kChunk * (cap + 1) >= (1ull << 32))
     return fail(ctx, PBF_ERR_INVALID, "n", "too many particles on one device (neighbour-list indexing)");
-  PBF_CUDA(ctx, ctx->nl.reserve((size_t)stride * (cap + 1)));
+  const uint32_t chunk_words = kChunk * (cap + 1);
+  PBF_CUDA(ctx, ctx->nl.reserve((size_t)n_chunks * chunk_words));
   PBF_CUDA(ctx, ctx->nl_count.reserve(n));
-  ctx->nl_stride = stride;
+  ctx->nl_stride = chunk_words;  // words per chunk of the list as this launch writes it (the delta pass reads it back)
   ctx->nl_cap = cap;
   if (cap == kListWide)
-    return launch_lambda_cap<kListWide>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride);
-  return launch_lambda_cap<kListMax>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, stride);
+    return launch_lambda_cap<kListWide>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, chunk_words);
+  return launch_lambda_cap<kListMax>(ctx, sel, keys_sorted, table, pos_mass, pstar_in, pstar_out, rho_out, chunk_words);
 }
 
 int launch_delta_list(pbf_ctx *ctx, const Sel &sel, const uint32_t *keys_sorted, const uint32_t *table,

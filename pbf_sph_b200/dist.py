@@ -203,59 +203,92 @@ def _profiled_group_steps(torch, dist, sr, p, steps, flags):
 def secondary_multi(torch, dist, args, device, rank, world, UNIT) -> list:
     """BASELINE.json configs[2] (dam-8m split over the N GPUs: strong scaling) and configs[4] (dam-weak-8m: ~8 M particles
     per GPU, 8 solver iterations: weak scaling), few steps each.  Rank 0 first measures the single-GPU figure each entry's
-    efficiency is quoted against (dam(200) with 4 and with 8 iterations) while the other ranks wait."""
+    efficiency is quoted against (dam(200) with 4 and with 8 iterations) while the other ranks wait.  A failure inside one
+    entry is reported in that entry (`error`) on every rank alike — it never takes the primary line down with it."""
     from . import scenes
     k = max(3, args.secondary_steps)
     single = {}
     if rank == 0:
-        p1, xs1 = scenes.dam_break(200, 4)
-        stream = torch.cuda.Stream()
-        with Solver(scenes.H, device, args.flags) as s:
-            s.set_stream(stream.cuda_stream)
-            s.upload(xs1)
-            del xs1
-            for _ in range(args.settle):
-                s.step(p1)
-            for iters in (4, 8):
-                p1.iteration = iters
-                for _ in range(3):
+        try:
+            p1, xs1 = scenes.dam_break(200, 4)
+            stream = torch.cuda.Stream()
+            with Solver(scenes.H, device, args.flags) as s:
+                s.set_stream(stream.cuda_stream)
+                s.upload(xs1)
+                del xs1
+                for _ in range(args.settle):
                     s.step(p1)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize()
-                e0.record(stream)
-                for _ in range(k):
-                    s.step(p1)
-                e1.record(stream)
-                torch.cuda.synchronize()
-                single[iters] = e0.elapsed_time(e1) / k
+                for iters in (4, 8):
+                    p1.iteration = iters
+                    for _ in range(3):
+                        s.step(p1)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    e0.record(stream)
+                    for _ in range(k):
+                        s.step(p1)
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                    single[iters] = e0.elapsed_time(e1) / k
+        except Exception as e:  # noqa: BLE001
+            single = {"error": repr(e)}
     box = [single]
     dist.broadcast_object_list(box, 0)
     single = box[0]
     out = []
     for name, side, iters, scaling in (("dam-8m", 200, 4, "strong"),
                                        ("dam-weak-8m", int(round((8_000_000 * world) ** (1 / 3))), 8, "weak")):
-        p, mine, n_total = scenes.dam_break_shard(side, iters, rank, world)
-        sr = _new_rank(torch, dist, device, rank, world, args.flags)
-        stream = torch.cuda.Stream()
-        sr.s.set_stream(stream.cuda_stream)
-        sr.upload(mine)
-        del mine
-        for _ in range(args.settle + 3):
-            sr.step(p)
-        ms = _timed_group_steps(torch, dist, sr, stream, p, k)
-        prof = _profiled_group_steps(torch, dist, sr, p, k, args.flags)
-        st = sr.stats()
+        sr, mine_result, err, n_total = None, None, None, side ** 3
+        try:
+            p, mine, n_total = scenes.dam_break_shard(side, iters, rank, world)
+            sr = _new_rank(torch, dist, device, rank, world, args.flags)
+            stream = torch.cuda.Stream()
+            sr.s.set_stream(stream.cuda_stream)
+            sr.upload(mine)
+            del mine
+            for _ in range(args.settle + 3):
+                sr.step(p)
+            # no torch collective inside the guarded region (a failed rank would leave its peers inside it): every rank times
+            # its own stream — the slab barriers inside the steps keep the ranks together — and the maximum is taken below
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(k):
+                sr.step(p)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            sr.s.set_flags(capi.FLAG_PROFILE | args.flags)
+            sr.s.profile_reset()
+            for _ in range(k):
+                sr.step(p)
+            torch.cuda.synchronize()
+            prof = sr.s.profile()
+            sr.s.set_flags(args.flags)
+            st = sr.stats()
+            mine_result = {"rank": rank, "owned": st["owned"], "ghosts": st["ghosts"], "ms_total": ms,
+                           "ms": {f: round(v / k, 4) for f, v in prof["ms"].items() if v > 0}}
+        except Exception as e:  # noqa: BLE001  (a rank that fails makes its peers' barriers time out: they land here too)
+            err = repr(e)
+        try:
+            if sr is not None:
+                sr.close()
+        except Exception:  # noqa: BLE001
+            pass
         ranks = [None] * world
-        dist.all_gather_object(ranks, {"rank": rank, "owned": st["owned"], "ghosts": st["ghosts"],
-                                       "ms": {f: round(v / k, 4) for f, v in prof["ms"].items() if v > 0}})
-        sr.close()
-        ms_step = ms / k
+        dist.all_gather_object(ranks, mine_result if err is None else {"rank": rank, "error": err})
+        workload_desc = f"dam-break {side}^3 = {n_total} particles, {iters} solver iterations, {world} GPUs"
+        if any("error" in r for r in ranks) or "error" in single:
+            out.append({"name": name, "workload": workload_desc, "n_gpus": world, "scaling": scaling,
+                        "error": [r["error"] for r in ranks if "error" in r] or single.get("error")})
+            continue
+        ms_step = max(r.pop("ms_total") for r in ranks) / k
         one = single[iters]  # dam(200) = 8 M particles on one GPU with the same iteration count
         if scaling == "strong":
             eff = one / (world * ms_step)
         else:  # weak: per-GPU work ~ constant; compare particle-iterations/s per GPU with the single-GPU run
             eff = (n_total * iters / ms_step / world) / (8_000_000 * iters / one)
-        out.append({"name": name, "workload": f"dam-break {side}^3 = {n_total} particles, {iters} solver iterations, {world} GPUs",
+        out.append({"name": name, "workload": workload_desc,
                     "n_gpus": world, "scaling": scaling, "particles": n_total, "solver_iterations": iters, "steps": k,
                     "settle_steps": args.settle, "ms_per_step": ms_step, "value": n_total * iters / (ms_step * 1e-3), "unit": UNIT,
                     "single_gpu": {"workload": f"dam-break 200^3 = 8000000 particles, {iters} solver iterations", "ms_per_step": one,
