@@ -165,7 +165,14 @@ private:
     const pbf_params p = toParams(config);
     uint64_t nv = 0;
     if (pbf_dist_advance_host(ctx, &p, reinterpret_cast<pbf_particle *>(xs.data()), xs.size(), &nv) != PBF_OK) raise("advance");
-    return {};
+    sph::Result<T, N, V> r;
+    if (nv) {  // the surface of the whole fluid, extracted on rank 0 from the lattice all ranks filled (same mesh as one device)
+      r.mesh.vs.resize(nv); r.mesh.ns.resize(nv); r.mesh.cs.resize(nv);
+      if (pbf_mesh_download(ctx, reinterpret_cast<float *>(r.mesh.vs.data()), reinterpret_cast<float *>(r.mesh.ns.data()),
+                            reinterpret_cast<float *>(r.mesh.cs.data()), nv) != PBF_OK)
+        raise("mesh download");
+    }
+    return r;
   }
 };
 

@@ -262,7 +262,11 @@ uint64_t pbf_launch_count(const pbf_ctx *ctx);
  *          (bench.py: torch.distributed.broadcast), every rank calls pbf_dist_init; ncclSend/ncclRecv groups.
  *   LOCAL  all ranks are contexts of ONE process (any devices, may share a device): pbf_dist_init_local;
  *          exchanges are device-to-device copies.  pbf_dist_step on any member steps the whole group.
- * Marching cubes is not available on the slab path (params->surface_enabled must be 0). */
+ * Marching cubes (params->surface_enabled): every rank evaluates the lattice points whose cell it owns — from its own
+ * particles and ring-1 ghosts, after one more push of the ghosts' final positions and diffused colours — straight into
+ * rank 0's lattice; rank 0 counts, scans and emits.  The mesh is the single-device mesh, bit for bit, and lives on rank 0
+ * (pbf_mesh_download / pbf_mesh_device on rank 0's context; the other ranks report no triangles).
+ * Scene dynamics (sources, drains, wells, queries) and the XSPH / vorticity extension are single-device only. */
 #define PBF_NCCL_ID_BYTES 128
 int pbf_dist_unique_id(uint8_t id[PBF_NCCL_ID_BYTES]);
 int pbf_dist_init(pbf_ctx *ctx, const uint8_t id[PBF_NCCL_ID_BYTES], int rank, int world);

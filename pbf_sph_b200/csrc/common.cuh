@@ -248,6 +248,7 @@ struct pbf_ctx {
   size_t pin_bytes = 0;
   // marching cubes
   pbf::DevBuf<float4> mc_pn, mc_c;
+  const float4 *mc_lattice_pn = nullptr, *mc_lattice_c = nullptr;  // the lattice of the last surface: mc_pn / mc_c, or the slab arena's
   pbf::DevBuf<uint32_t> mc_count, mc_offset;
   pbf::DevBuf<float> mesh_vs, mesh_ns, mesh_cs;
   uint32_t *mc_total_dev = nullptr;   // device word: total triangles
@@ -366,6 +367,11 @@ int launch_xsph_vorticity(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint3
                           float4 *scratch_omega, float4 *scratch_vel);
 int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *total_out_dev);
 int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col);
+// the same in three parts (slab path: every rank evaluates the lattice points it owns into rank 0's lattice, rank 0 extracts)
+int mc_prepare(pbf_ctx *ctx, const pbf_params &p);
+int mc_field(pbf_ctx *ctx, const uint32_t *table, const float4 *pos, const float4 *col, float4 *PN, float4 *LC, uint32_t key_lo,
+             uint32_t key_hi);
+int mc_extract(pbf_ctx *ctx, const float4 *PN, const float4 *LC);
 
 void dist_release(pbf_ctx *ctx);  // dist.cu
 int dist_refresh_counts(pbf_ctx *ctx);  // slab rank: wait for the last step and refresh ctx->n from the device-side counts

@@ -572,7 +572,8 @@ int pbf_grid(pbf_ctx *ctx, pbf_grid_info *out) {
 int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes) {
   PBF_ENTER(ctx);
   if (!dst) return fail(ctx, PBF_ERR_INVALID, "dst", "NULL");
-  if (ctx->dist) return fail(ctx, PBF_ERR_STATE, "pbf_debug_read", "taps are single-device (a slab rank's arrays are laid out by the arena)");
+  if (ctx->dist && tap != PBF_TAP_MC_FIELD && tap != PBF_TAP_MC_COLOUR)  // the surface lattice is not a particle array
+    return fail(ctx, PBF_ERR_STATE, "pbf_debug_read", "taps are single-device (a slab rank's arrays are laid out by the arena)");
   PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   const uint64_t n = ctx->n;
   const void *src = nullptr;
@@ -589,8 +590,8 @@ int pbf_debug_read(pbf_ctx *ctx, int tap, void *dst, uint64_t dst_bytes) {
     case PBF_TAP_LAMBDA: src = ctx->pstar[1].p; bytes = n * 4; strided_w = true; break;
     case PBF_TAP_RHO: src = ctx->rho.p; bytes = n * 4; break;
     case PBF_TAP_IDS: src = ctx->ids[ctx->cur].p; bytes = n * 8; break;
-    case PBF_TAP_MC_FIELD: src = ctx->mc_pn.p; bytes = ctx->mc_valid ? ctx->mc.lattice_n * 16 : 0; break;
-    case PBF_TAP_MC_COLOUR: src = ctx->mc_c.p; bytes = ctx->mc_valid ? ctx->mc.lattice_n * 16 : 0; break;
+    case PBF_TAP_MC_FIELD: src = ctx->mc_lattice_pn; bytes = ctx->mc_valid ? ctx->mc.lattice_n * 16 : 0; break;
+    case PBF_TAP_MC_COLOUR: src = ctx->mc_lattice_c; bytes = ctx->mc_valid ? ctx->mc.lattice_n * 16 : 0; break;
     default: return fail(ctx, PBF_ERR_INVALID, "tap", "unknown");
   }
   if (!src || bytes == 0) return fail(ctx, PBF_ERR_STATE, "pbf_debug_read", "tap not available (no step run, or flag not set)");

@@ -124,6 +124,8 @@ struct ArenaLayout {
   uint32_t cap_g = 0, cap_own = 0, cap_local = 0, own_off = 0;  // cap_local = cap_g + cap_own + cap_g
   uint32_t world = 1, row_words = 0;
   size_t pos[2]{}, vel[2]{}, col[2]{}, pstar0 = 0, ids[2]{}, keys_local = 0, k2 = 0, halo[2]{}, rows[2]{}, flags = 0, bytes = 0;
+  uint64_t cap_lattice = 0;       // marching cubes: lattice points the two arrays below hold (0 until a surface is asked for)
+  size_t mc_pn = 0, mc_lc = 0;    // the surface lattice (field | normal, colour): every rank stores its points into rank 0's
 };
 
 struct PeerTable {
@@ -167,6 +169,7 @@ struct pbf_dist_state {
   DevBuf<float4> pstar1;
   bool diffuse_pending = false;
   uint32_t cnt_nblk = 0;                          // tile stride of blk_cnt as its last count pass wrote it (the arena may grow before the scatter)
+  uint64_t want_lattice = 0;                      // lattice points the next arena build must hold (marching cubes)
   uint32_t send_plan = 0;                         // send-list entries the last plan sized for (the same on every rank)
   // early re-plan: the `hot` verdict of every step comes back through a small ring of pinned words, read two steps later
   // (all ranks read the verdict of the SAME step, so they still agree on which steps are plan steps without talking)
@@ -594,6 +597,25 @@ __global__ void ghost_fix_kernel(const SlabDyn *__restrict__ dyn, ArenaLayout la
   pstar[i] = p;
 }
 
+// Marching cubes on the slab path: the owners' FINAL positions (pStar * scale, the finalise arithmetic, with the mass) and
+// DIFFUSED colours of the send list -> the ghost slots of the destination's position / colour arrays.  Runs after a barrier
+// behind every rank's finalise (nobody reads those slots any more in this step).
+__global__ void push_surface_kernel(const SlabDyn *__restrict__ dyn, PeerTable peers, ArenaLayout lay, int cur, int cur_col, int world,
+                                    float scale, const uint32_t *__restrict__ send_idx, const float4 *__restrict__ pstar,
+                                    const float4 *__restrict__ pos_mass, const float4 *__restrict__ col) {
+  const uint32_t j = blockIdx.x * kBlk + threadIdx.x;
+  if (j >= dyn->n_send) return;
+  int q = 0;
+  while (q + 1 < world && j >= dyn->gh_send_off[q + 1]) ++q;
+  const size_t at = (size_t)dyn->gh_dst[q] + (j - dyn->gh_send_off[q]);
+  if (at >= lay.cap_local) return;
+  const uint32_t i = lay.own_off + __ldg(send_idx + j);
+  const float4 p = ldg4(pstar + i);
+  char *base = peers.base[q];
+  arena_ptr<float4>(base, lay.pos[cur])[at] = make_float4(fmul(p.x, scale), fmul(p.y, scale), fmul(p.z, scale), __ldg(&pos_mass[i].w));
+  arena_ptr<float4>(base, lay.col[cur_col])[at] = ldg4(col + i);
+}
+
 // Role of every particle of the local array for the solver passes (static within a step), as per-tile counts for the
 // two compact lists the passes run over (the interior pass runs over the owned range in place, skipping the boundary):
 //   ring-1 ghosts   a ghost one of whose 27 cells is ours: lambda is computed here (besides the owned particles)
@@ -783,7 +805,7 @@ int all_gather_host(std::vector<pbf_ctx *> &L, const std::vector<uint64_t> &mine
 // ------------------------------------------------------------------------------------------------- arena
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-ArenaLayout make_layout(uint32_t cap_g, uint32_t cap_own, int world) {
+ArenaLayout make_layout(uint32_t cap_g, uint32_t cap_own, int world, uint64_t cap_lattice) {
   ArenaLayout l;
   // Capacities are multiples of 256 elements: the owned block starts at element cap_g of every array, and the solver
   // passes index the neighbour-list rows, pStar and the keys by that position — a warp's 32 consecutive particles must
@@ -801,6 +823,9 @@ ArenaLayout make_layout(uint32_t cap_g, uint32_t cap_own, int world) {
   for (int i = 0; i < 2; ++i) l.ids[i] = take((size_t)l.cap_local * 8);
   l.keys_local = take((size_t)l.cap_local * 4);
   l.k2 = take((size_t)l.cap_local * 4);
+  l.cap_lattice = cap_lattice;
+  l.mc_pn = take((size_t)cap_lattice * 16);
+  l.mc_lc = take((size_t)cap_lattice * 16);
   for (int i = 0; i < 2; ++i) l.halo[i] = take((size_t)2 * cap_g * 16);
   for (int i = 0; i < 2; ++i) l.rows[i] = take((size_t)world * l.row_words * 4);
   l.flags = take((size_t)2 * kMaxWorld * 4);  // barrier flags: [main | comm stream][source rank], zeroed with the rows
@@ -825,7 +850,7 @@ int build_arenas(std::vector<pbf_ctx *> &L, uint32_t cap_g, uint32_t cap_own, co
     pbf_ctx *c = L[r];
     D *d = c->dist;
     PBF_CUDA(c, cudaSetDevice(c->device));
-    const ArenaLayout nl = make_layout(cap_g, cap_own, W);
+    const ArenaLayout nl = make_layout(cap_g, cap_own, W, std::max(d->lay.cap_lattice, d->want_lattice));
     char *fresh = nullptr;
     PBF_CUDA(c, cudaMalloc(&fresh, nl.bytes));
     PBF_CUDA(c, cudaMemsetAsync(fresh + nl.rows[0], 0, nl.bytes - nl.rows[0], c->stream));
@@ -1204,11 +1229,56 @@ int regrow(std::vector<pbf_ctx *> &L, uint32_t cap_g, uint32_t cap_own, const st
   return PBF_OK;
 }
 
+// Marching cubes of the whole fluid (ompsph.hpp:277-477) on the slab path.  A lattice point is evaluated by the rank that
+// owns its cell (clamped into the grid): that rank holds every particle of the 27 cells the point looks at — its own and
+// ring-1 ghosts — in the single-device order, so the sums are the single-device sums.  Ghosts need their FINAL positions
+// and DIFFUSED colours first (one more 32-byte-per-ghost push).  All ranks store their points straight into rank 0's
+// lattice (peer memory); rank 0 counts, scans and emits the triangles: the mesh is the single-device mesh, bit for bit.
+int slab_surface(std::vector<pbf_ctx *> &L, const pbf_params &p) {
+  D *d0 = L[0]->dist;
+  const int W = d0->world;
+  if (W > 1) {
+    PBF_TRY(barrier(L, 0));  // every rank is past its iterations, its diffusion and its finalise
+    for (pbf_ctx *c : L) {
+      D *d = c->dist;
+      const ArenaLayout &l = d->lay;
+      PBF_CUDA(c, cudaSetDevice(c->device));
+      PhaseScope ps(c, PBF_PH_HALO);
+      push_surface_kernel<<<div_up(d->send_idx.cap, kBlk), kBlk, 0, c->stream>>>(d->dyn, d->peers, l, c->cur, c->cur_col, W, p.scale, d->send_idx.p,
+                                                                                c->pstar[0].p, c->pos[c->cur].p, c->col[c->cur_col].p);
+      PBF_LAUNCH_CHECK(c);
+    }
+    PBF_TRY(barrier(L, 0));
+  }
+  for (pbf_ctx *c : L) {
+    D *d = c->dist;
+    const ArenaLayout &l = d->lay;
+    PBF_CUDA(c, cudaSetDevice(c->device));
+    if (c->mc.lattice_n > l.cap_lattice) return fail(c, PBF_ERR_STATE, "slab surface", "lattice larger than the arena's (plan step missed)");
+    char *root = d->peers.base[0];  // rank 0's arena as this rank addresses it
+    const uint32_t lo = W > 1 ? d->splits[d->rank] : 0u, hi = W > 1 ? d->splits[d->rank + 1] : 0xFFFFFFFFu;
+    c->sc.n = l.cap_local;
+    c->sc.n_dyn = nullptr;
+    PBF_TRY(mc_field(c, c->table.p, c->pos[c->cur].p, c->col[c->cur_col].p, arena_ptr<float4>(root, l.mc_pn), arena_ptr<float4>(root, l.mc_lc), lo, hi));
+  }
+  if (W > 1) PBF_TRY(barrier(L, 0));
+  for (pbf_ctx *c : L) {
+    D *d = c->dist;
+    PBF_CUDA(c, cudaSetDevice(c->device));
+    c->n_triangles = 0;
+    c->mc_valid = false;
+    if (d->rank != 0) continue;
+    c->mc_lattice_pn = arena_ptr<float4>(d->arena, d->lay.mc_pn);
+    c->mc_lattice_c = arena_ptr<float4>(d->arena, d->lay.mc_lc);
+    PBF_TRY(mc_extract(c, c->mc_lattice_pn, c->mc_lattice_c));
+  }
+  return PBF_OK;
+}
+
 int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
   D *d0 = L[0]->dist;
   const int W = d0->world;
   for (pbf_ctx *c : L) {
-    if (p.surface_enabled) return fail(c, PBF_ERR_INVALID, "pbf_dist_step", "marching cubes is not available on the slab path");
     if (c->flags & PBF_FLAG_GLOBAL_NEIGHBOURS) return fail(c, PBF_ERR_STATE, "pbf_dist_step", "PBF_FLAG_GLOBAL_NEIGHBOURS is single-device only");
     host_grid(c->h, p, c->grid);
     for (int a = 0; a < 3; ++a)
@@ -1218,6 +1288,18 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
   }
   bool any_fresh = false;
   for (pbf_ctx *c : L) any_fresh |= c->dist->fresh;
+  // marching cubes: the lattice lives in the arena (rank 0's is the one everybody stores into); every rank derives the
+  // same size from the same parameters, so a larger lattice makes this a plan step on every rank without talking
+  bool lattice_grow = false;
+  if (p.surface_enabled) {
+    for (pbf_ctx *c : L) {
+      PBF_TRY(mc_prepare(c, p));
+      if (c->mc.lattice_n > c->dist->lay.cap_lattice) {
+        c->dist->want_lattice = c->mc.lattice_n + c->mc.lattice_n / 4;
+        lattice_grow = true;
+      }
+    }
+  }
   // NCCL ranks agree on "is this a plan step" without talking: uploads are collective by contract and the schedule is a
   // function of the step index.
   // ... and of the `hot` verdict of the step two back (identical on every rank; a verdict older than the last plan is stale).
@@ -1232,7 +1314,7 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
     }
   }
   const bool replan = d0->splits.empty() || hot || (d0->replan_every && d0->step_index % d0->replan_every == 0);
-  const bool plan = replan || any_fresh || !d0->arena;
+  const bool plan = replan || any_fresh || !d0->arena || lattice_grow;
   const bool measure = d0->replan_every && (d0->step_index + 1) % d0->replan_every == 0 && p.iteration <= (uint64_t)kMaxTimedIters;
 
   if (plan) {
@@ -1253,7 +1335,7 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
     const uint64_t want_own = std::max<uint64_t>(max_held, (total + W - 1) / W) + 256;
     const uint64_t want_g = d0->arena ? 0 : std::max<uint64_t>(1024, want_own / 3);
     uint32_t cap_g, cap_own;
-    if (need_growth(d0->lay, want_own, want_g, cap_g, cap_own) || !d0->arena) {
+    if (need_growth(d0->lay, want_own, want_g, cap_g, cap_own) || !d0->arena || lattice_grow) {
       std::vector<uint64_t> live(L.size(), 0);
       for (size_t r = 0; r < L.size(); ++r) live[r] = L[r]->dist->fresh ? 0 : held[r];
       PBF_TRY(build_arenas(L, std::max(cap_g, 1u), std::max(cap_own, 1u), live));
@@ -1430,6 +1512,13 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
     PBF_TRY(launch_finalise(c, c->pstar[0].p + l.own_off, c->pos[c->cur].p + l.own_off, c->vel[c->cur].p + l.own_off));
     c->sc.n = l.cap_local;
     c->sc.n_dyn = nullptr;
+    c->n_triangles = 0;
+    c->mc_valid = false;
+  }
+  if (p.surface_enabled) PBF_TRY(slab_surface(L, p));
+  for (pbf_ctx *c : L) {
+    D *d = c->dist;
+    PBF_CUDA(c, cudaSetDevice(c->device));
     // the next step starts from this step's owned particles; the mirror serves statistics, downloads and plan steps
     next_step_kernel<<<1, 32, 0, c->stream>>>(d->dyn);
     PBF_LAUNCH_CHECK(c);
@@ -1726,6 +1815,7 @@ int pbf_dist_advance_host(pbf_ctx *ctx, const pbf_params *params, pbf_particle *
   if (off != n) return fail(ctx, PBF_ERR_STATE, "pbf_dist_advance_host", "particle count changed");
   PBF_TRY(sync_all(L));
   d0->last_counts = cnt;
+  if (n_mesh_vertices) *n_mesh_vertices = L[0]->n_triangles * 3;  // marching cubes: rank 0 holds the mesh (pbf_mesh_download)
   return PBF_OK;
 }
 

@@ -36,10 +36,12 @@ __device__ __forceinline__ float glm_fast_sqrt(float x) { return fdiv(1.0f, fdiv
 constexpr int kFieldCap = 48;    // hits a point can hold; a full list is evaluated on the spot (rare: one lane works)
 constexpr int kFieldFlush = 32;  // after each cell: if ANY lane holds this many, the whole warp evaluates its lists
 
+// [key_lo, key_hi): the slab path's ownership filter — a rank evaluates the lattice points whose cell (clamped into the
+// grid) it owns, and stores them into rank 0's lattice; one device passes [0, 2^32).
 __global__ void __launch_bounds__(kMcBlock) mc_field_kernel(StepConst c, McConst m, const uint32_t *__restrict__ table,
                                                             const float4 *__restrict__ pos,
                                                             const float4 *__restrict__ col, float4 *__restrict__ PN,
-                                                            float4 *__restrict__ LC) {
+                                                            float4 *__restrict__ LC, uint32_t key_lo, uint32_t key_hi) {
   __shared__ uint32_t s_list[kFieldCap * kMcBlock];  // [slot][thread]: conflict-free
   const uint32_t tid = threadIdx.x;
   const uint32_t ntz = (m.sample[2] + 7u) / 8u, nty = (m.sample[1] + 3u) / 4u;
@@ -56,6 +58,12 @@ __global__ void __launch_bounds__(kMcBlock) mc_field_kernel(StepConst c, McConst
   for (int k = 0; k < 3; ++k) {
     a[k] = fmul(fadd(c.min_extent[k], fmul(lp[k], m.step)), c.scale);                       // ompsph.hpp:291
     c0[k] = (int)compact10(spread10(cell_coord(fdiv(lp[k], m.resolution))));                // ompsph.hpp:294-299
+  }
+  if (alive && key_hi - key_lo != 0xFFFFFFFFu) {  // slab path: is this lattice point mine?
+    const uint32_t cc[3] = {min((uint32_t)c0[0], c.extent[0] - 1u), min((uint32_t)c0[1], c.extent[1] - 1u),
+                            min((uint32_t)c0[2], c.extent[2] - 1u)};
+    const uint32_t key = spread10(cc[0]) | (spread10(cc[1]) << 1) | (spread10(cc[2]) << 2);
+    alive = key >= key_lo && key < key_hi;
   }
   if (alive && (uint32_t)c0[0] == c.extent[0] && (uint32_t)c0[1] == c.extent[1] && (uint32_t)c0[2] == c.extent[2]) {
     PN[idx] = make_float4(0.f, 0.f, 0.f, 0.f);  // ompsph.hpp:301-304: the entry keeps its zero initialisation
@@ -208,7 +216,8 @@ __global__ void __launch_bounds__(kMcBlock) mc_emit_kernel(StepConst c, McConst 
 
 }  // namespace
 
-int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col) {
+// constants of this step's surface (McParams -> McConst) and the lattice sizes; no device work
+int mc_prepare(pbf_ctx *ctx, const pbf_params &p) {
   McConst &m = ctx->mc;
   m.resolution = p.surface.resolution;
   m.isolevel = p.surface.isolevel;
@@ -238,23 +247,33 @@ int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float
   m.lattice_n = (uint64_t)m.sample[0] * m.sample[1] * m.sample[2];
   m.march_n = (uint64_t)m.march[0] * m.march[1] * m.march[2];
   if (m.lattice_n >= (1ull << 32)) return fail(ctx, PBF_ERR_INVALID, "surface", "lattice too large");
-  PBF_CUDA(ctx, ctx->mc_pn.reserve(m.lattice_n));
-  PBF_CUDA(ctx, ctx->mc_c.reserve(m.lattice_n));
-  PBF_CUDA(ctx, ctx->mc_count.reserve(m.march_n + 1));
-  PBF_CUDA(ctx, ctx->mc_offset.reserve(m.march_n + 1));
-  {
-    PhaseScope ps(ctx, PBF_PH_MC_FIELD);
-    const uint64_t tiles = (uint64_t)((m.sample[0] + 3u) / 4u) * ((m.sample[1] + 3u) / 4u) * ((m.sample[2] + 7u) / 8u);
-    if (tiles >= (1ull << 31)) return fail(ctx, PBF_ERR_INVALID, "surface", "lattice too large");
-    mc_field_kernel<<<(unsigned)tiles, kMcBlock, 0, ctx->stream>>>(ctx->sc, m, table, pos, col, ctx->mc_pn.p, ctx->mc_c.p);
-    PBF_LAUNCH_CHECK(ctx);
-  }
+  const uint64_t tiles = (uint64_t)((m.sample[0] + 3u) / 4u) * ((m.sample[1] + 3u) / 4u) * ((m.sample[2] + 7u) / 8u);
+  if (tiles >= (1ull << 31)) return fail(ctx, PBF_ERR_INVALID, "surface", "lattice too large");
+  return PBF_OK;
+}
+
+// scalar field / normal / colour of the lattice points whose cell key lies in [key_lo, key_hi) -> PN, LC (lattice_n each)
+int mc_field(pbf_ctx *ctx, const uint32_t *table, const float4 *pos, const float4 *col, float4 *PN, float4 *LC, uint32_t key_lo,
+             uint32_t key_hi) {
+  const McConst &m = ctx->mc;
+  PhaseScope ps(ctx, PBF_PH_MC_FIELD);
+  const uint64_t tiles = (uint64_t)((m.sample[0] + 3u) / 4u) * ((m.sample[1] + 3u) / 4u) * ((m.sample[2] + 7u) / 8u);
+  mc_field_kernel<<<(unsigned)tiles, kMcBlock, 0, ctx->stream>>>(ctx->sc, m, table, pos, col, PN, LC, key_lo, key_hi);
+  PBF_LAUNCH_CHECK(ctx);
+  return PBF_OK;
+}
+
+// triangles from a complete lattice: count, scan, emit (deterministic order: ascending cube index)
+int mc_extract(pbf_ctx *ctx, const float4 *PN, const float4 *LC) {
+  const McConst &m = ctx->mc;
   ctx->mc_valid = true;
   ctx->mc_total_host[0] = 0;
   if (m.march_n == 0) { ctx->n_triangles = 0; return PBF_OK; }
+  PBF_CUDA(ctx, ctx->mc_count.reserve(m.march_n + 1));
+  PBF_CUDA(ctx, ctx->mc_offset.reserve(m.march_n + 1));
   {
     PhaseScope ps(ctx, PBF_PH_MC_COUNT_SCAN);
-    mc_count_kernel<<<div_up(m.march_n, kMcBlock), kMcBlock, 0, ctx->stream>>>(m, ctx->mc_pn.p, ctx->mc_count.p);
+    mc_count_kernel<<<div_up(m.march_n, kMcBlock), kMcBlock, 0, ctx->stream>>>(m, PN, ctx->mc_count.p);
     PBF_LAUNCH_CHECK(ctx);
     PBF_TRY(exclusive_scan_u32(ctx, ctx->mc_count.p, ctx->mc_offset.p, m.march_n, ctx->mc_total_dev));
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->mc_total_host, ctx->mc_total_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -271,13 +290,21 @@ int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float
   PBF_CUDA(ctx, ctx->mesh_cs.reserve(ctx->n_triangles * 12));
   {
     PhaseScope ps(ctx, PBF_PH_MC_EMIT);
-    mc_emit_kernel<<<div_up(m.march_n, kMcBlock), kMcBlock, 0, ctx->stream>>>(ctx->sc, m, ctx->mc_pn.p, ctx->mc_c.p,
-                                                                             ctx->mc_count.p, ctx->mc_offset.p,
-                                                                             ctx->mesh_vs.p, ctx->mesh_ns.p,
-                                                                             ctx->mesh_cs.p);
+    mc_emit_kernel<<<div_up(m.march_n, kMcBlock), kMcBlock, 0, ctx->stream>>>(ctx->sc, m, PN, LC, ctx->mc_count.p, ctx->mc_offset.p,
+                                                                             ctx->mesh_vs.p, ctx->mesh_ns.p, ctx->mesh_cs.p);
     PBF_LAUNCH_CHECK(ctx);
   }
   return PBF_OK;
+}
+
+int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col) {
+  PBF_TRY(mc_prepare(ctx, p));
+  PBF_CUDA(ctx, ctx->mc_pn.reserve(ctx->mc.lattice_n));
+  PBF_CUDA(ctx, ctx->mc_c.reserve(ctx->mc.lattice_n));
+  ctx->mc_lattice_pn = ctx->mc_pn.p;
+  ctx->mc_lattice_c = ctx->mc_c.p;
+  PBF_TRY(mc_field(ctx, table, pos, col, ctx->mc_pn.p, ctx->mc_c.p, 0u, 0xFFFFFFFFu));
+  return mc_extract(ctx, ctx->mc_pn.p, ctx->mc_c.p);
 }
 
 }  // namespace pbf

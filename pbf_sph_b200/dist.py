@@ -101,12 +101,18 @@ class LocalGroup:
         s = self.solvers[0]
         s._ck(s._L.pbf_dist_step(s._ctx, C.byref(params)))
 
-    def advance(self, params: Params, xs: np.ndarray) -> None:
-        """sph::Solver::advance over the group: `xs` in place, back in the global Z order (pbf_dist_advance_host)."""
+    def advance(self, params: Params, xs: np.ndarray) -> int:
+        """sph::Solver::advance over the group (returns the mesh vertex count): `xs` in place, back in the global Z order (pbf_dist_advance_host)."""
         assert xs.dtype == PARTICLE and xs.flags.c_contiguous
         s = self.solvers[0]
         nv = C.c_uint64(0)
         s._ck(s._L.pbf_dist_advance_host(s._ctx, C.byref(params), xs.ctypes.data, len(xs), C.byref(nv)))
+        return int(nv.value)
+
+    def mesh(self):
+        """The surface of the last step (params.surface_enabled): every rank fills the lattice points it owns, rank 0
+        extracts the triangles — the single-device mesh."""
+        return self.solvers[0].mesh()
 
     def sync(self) -> None:
         for s in self.solvers:

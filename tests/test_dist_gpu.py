@@ -91,15 +91,12 @@ def test_slab_rank_with_uneven_and_empty_uploads(gpu):
     assert np.array_equal(by_id(ref[-1])["position"].view(np.uint32), by_id(out)["position"].view(np.uint32))
 
 
-def test_slab_path_rejects_surface_and_single_device_calls(gpu):
+def test_slab_path_rejects_single_device_calls(gpu):
     p, xs = scenes.two_cubes(2000, 2)
     with LocalGroup(H, [0, 0]) as g:
         g.upload(xs)
         with pytest.raises(capi.PbfError):
             g.solvers[0].step(p)  # pbf_step on a slab rank
-        p.surface_enabled = 1
-        with pytest.raises(capi.PbfError):
-            g.step(p)
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -140,3 +137,53 @@ def test_group_on_distinct_devices(gpu):
             g.step(scenes.apply_motion(p, f))
         out = g.download()
     assert out.tobytes() == ref[-1].tobytes()
+
+
+@pytest.mark.parametrize("world,replan", [(2, 4), (3, 1), (4, 2)])
+def test_slab_group_surface_is_the_single_device_mesh(gpu, world, replan):
+    """Marching cubes on the slab path (ompsph.hpp:277-477): lattice NaN pattern, triangle count and every vertex, normal
+    and colour equal the single-device surface bit for bit, on the moving-wall scene (the lattice changes size between
+    frames, which re-plans the arenas)."""
+    p, xs = scenes.two_cubes(20000, 3)
+    frames = 5
+    ref = []
+    with Solver(H, 0) as s:
+        s.upload(xs.copy())
+        for f in range(frames):
+            pf = scenes.apply_motion(p, f)
+            pf.surface_enabled = 1
+            s.step(pf)
+            ref.append((s.download(), s.mesh(), s.tap(capi.TAP_MC_FIELD).copy()))
+    with LocalGroup(H, [0] * world) as g:
+        g.ranks[0].set_replan(replan)
+        g.upload(xs.copy())
+        for f in range(frames):
+            pf = scenes.apply_motion(p, f)
+            pf.surface_enabled = 1
+            g.step(pf)
+            got, mesh = g.download(), g.mesh()
+            a, m, field = ref[f]
+            assert np.array_equal(a["id"], got["id"]) and np.array_equal(a["position"].view(np.uint32), got["position"].view(np.uint32))
+            lattice = g.solvers[0].tap(capi.TAP_MC_FIELD)
+            assert np.array_equal(field.view(np.uint32), lattice.view(np.uint32)), f"frame {f}: lattice differs"
+            assert len(mesh.vs) == len(m.vs) and len(m.vs) > 0, f"frame {f}: {len(mesh.vs)} vertices, one device has {len(m.vs)}"
+            for name in ("vs", "ns", "cs"):
+                assert np.array_equal(getattr(m, name).view(np.uint32), getattr(mesh, name).view(np.uint32)), f"frame {f}: mesh.{name} differs"
+            # only rank 0 holds the mesh
+            assert all(s_.grid().n_triangles == 0 for s_ in g.solvers[1:])
+
+
+def test_slab_group_advance_returns_the_mesh(gpu):
+    """pbf_dist_advance_host (the multi-device sph::Solver::advance) with a surface: vertex count and mesh of one device."""
+    p, xs = scenes.two_cubes(20000, 3)
+    p.surface_enabled = 1
+    one = xs.copy()
+    with Solver(H, 0) as s:
+        res = s.advance(p, one)
+    many = xs.copy()
+    with LocalGroup(H, [0, 0, 0]) as g:
+        nv = g.advance(p, many)
+        mesh = g.mesh()
+    assert nv == len(res.vs) and nv > 0
+    assert np.array_equal(one["id"], many["id"])
+    assert np.array_equal(res.vs.view(np.uint32), mesh.vs.view(np.uint32))
