@@ -257,11 +257,14 @@ uint64_t pbf_launch_count(const pbf_ctx *ctx);
 /* ---- multi-GPU: Z-curve slab decomposition, one rank per GPU ----------------------------------------- */
 /* The reference is single-device; this is the north-star extension.  Rank r owns the
  * Morton key range [split[r], split[r+1]); per step: migrants to their owners, then a 2-cell ghost layer whose
- * pStar is refreshed once per solver iteration.  Two transports:
+ * pStar is refreshed once per solver iteration.  Every exchange is a kernel that stores into the peer's memory (each
+ * rank's arrays live in one arena that all peers map) followed by a flag barrier on the stream; all counts stay on the
+ * device, so an ordinary step never waits for the host.  Two ways to form the group:
  *   NCCL   one process per GPU: rank 0 makes the id (pbf_dist_unique_id), the launcher distributes it
- *          (bench.py: torch.distributed.broadcast), every rank calls pbf_dist_init; ncclSend/ncclRecv groups.
+ *          (bench.py: torch.distributed.broadcast), every rank calls pbf_dist_init.  NCCL carries the bootstrap (CUDA IPC
+ *          handles of the arenas) and the key-histogram all-reduce of the plan steps; the data moves by peer stores.
  *   LOCAL  all ranks are contexts of ONE process (any devices, may share a device): pbf_dist_init_local;
- *          exchanges are device-to-device copies.  pbf_dist_step on any member steps the whole group.
+ *          peers are addressed directly, barriers are CUDA events.  pbf_dist_step on any member steps the whole group.
  * Marching cubes (params->surface_enabled): every rank evaluates the lattice points whose cell it owns — from its own
  * particles and ring-1 ghosts, after one more push of the ghosts' final positions and diffused colours — straight into
  * rank 0's lattice; rank 0 counts, scans and emits.  The mesh is the single-device mesh, bit for bit, and lives on rank 0

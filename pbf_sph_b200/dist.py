@@ -396,7 +396,7 @@ def bench_main(args, workload, ClockSampler, METRIC, UNIT, roofline_of=None) -> 
             "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "name": name, "particles": n_total, "solver_iterations": iters,
-                       "settle_steps": args.settle, "decomposition": "Z-curve slabs, NCCL send/recv halo per solver iteration",
+                       "settle_steps": args.settle, "decomposition": "Z-curve slabs; migrants, ghosts and the per-iteration halo (16 B per ghost) move by kernels storing into peer memory over NVLink (arenas mapped through CUDA IPC), flag barriers on the stream; NCCL for the bootstrap and the plan steps' histogram all-reduce",
                        "l2": "no flush: the per-step working set exceeds the 126 MB L2"},
             "particle_steps_per_sec": n_total * args.steps / (ms_total * 1e-3),
             # rank 0's dominant kernel family over the particles rank 0 processes (owned + ghosts)

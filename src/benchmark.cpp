@@ -197,10 +197,6 @@ int main(int argc, char *argv[]) {
     if (o.devices.empty()) o.devices.push_back(0);
     if (o.devices.size() > 1 && (o.resident || o.fountain))
       throw std::runtime_error("--resident and --fountain drive a single device");
-    if (o.devices.size() > 1 && o.surface) {
-      std::cout << "surface extraction is a single-device feature: disabled for the " << o.devices.size() << "-device run" << std::endl;
-      o.surface = false;
-    }
     sph::cuda_impl::Solver<size_t, float, pbf::vec> solver(0.1f, o.devices, o.pin);  // h = 0.1, benchmark.cpp:160-163
     const float scaling = 500;  // benchmark.cpp:25
     auto [mc, param, particles] = o.scene == "dam"

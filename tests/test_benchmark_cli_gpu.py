@@ -131,11 +131,14 @@ def test_device_list_runs_the_slab_path_and_matches_one_device(gpu, tmp_path):
     assert "Final Particle count : 64000" in four.stdout
     a, b = (tmp_path / "one_4" / "cloud.ply").read_bytes(), (tmp_path / "four_4" / "cloud.ply").read_bytes()
     assert len(a) > 64000 * 32 and a == b
-    # the stock scene with its moving wall, surface requested: the slab run says it drops the surface and still matches
+    # the stock scene with its moving wall and the surface on (the stock benchmark, benchmark.cpp:29): particles AND mesh of
+    # the two-rank run are the single-device files byte for byte
     stock = ["--particles=20000", "--solver-iters=4", "-n", "3", "-w", "2"]
-    one = run(*stock, "--surface=off", "-o", str(tmp_path / "s1_{iter}"))
+    one = run(*stock, "-o", str(tmp_path / "s1_{iter}"))
     two = run(*stock, "-d", "0,0", "-o", str(tmp_path / "s2_{iter}"))
     assert one.returncode == 0 and two.returncode == 0, one.stderr + two.stderr
     assert (tmp_path / "s1_3" / "cloud.ply").read_bytes() == (tmp_path / "s2_3" / "cloud.ply").read_bytes()
+    mesh = (tmp_path / "s1_3" / "mesh.obj").read_bytes()
+    assert len(mesh) > 10000 and mesh == (tmp_path / "s2_3" / "mesh.obj").read_bytes()
     assert run("--gpus=2", "--resident", "-n1", "-w0", "-o", "").returncode != 0
     assert run("-d", "0,99", "-n1", "-w0", "-o", "").returncode != 0  # no such device
