@@ -294,6 +294,9 @@ typedef struct pbf_dist_stats {
   uint32_t key_lo, key_hi;                           /* owned Morton range */
   uint32_t ghost_ring1;                              /* ghosts whose lambda is computed locally */
   uint32_t boundary;                                 /* owned particles some other rank holds as ghosts */
+  uint32_t plan_steps;                               /* plan steps so far (scheduled, after uploads, and early ones) */
+  uint32_t early_plans;                              /* ... of which forced by a capacity watermark */
+  uint32_t capacity_owned, capacity_ghosts;          /* particles the arena holds: owned block, each ghost block */
 } pbf_dist_stats;
 int pbf_dist_stats_read(pbf_ctx *ctx, pbf_dist_stats *out);
 

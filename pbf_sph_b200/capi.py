@@ -68,7 +68,8 @@ class Profile(C.Structure):
 class DistStats(C.Structure):
     _fields_ = [("owned", C.c_uint64), ("ghosts", C.c_uint64), ("migrants_out", C.c_uint64),
                 ("migrants_in", C.c_uint64), ("halo_bytes_per_iteration", C.c_uint64), ("key_lo", C.c_uint32),
-                ("key_hi", C.c_uint32), ("ghost_ring1", C.c_uint32), ("boundary", C.c_uint32)]
+                ("key_hi", C.c_uint32), ("ghost_ring1", C.c_uint32), ("boundary", C.c_uint32), ("plan_steps", C.c_uint32),
+                ("early_plans", C.c_uint32), ("capacity_owned", C.c_uint32), ("capacity_ghosts", C.c_uint32)]
 
 
 class Well(C.Structure):  # sph::Well — sph.hpp:56-60

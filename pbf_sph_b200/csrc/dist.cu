@@ -177,6 +177,7 @@ struct pbf_dist_state {
   uint32_t *h_hot = nullptr;
   cudaEvent_t ev_step[kHotRing] = {};
   uint64_t last_plan_step = 0;
+  uint32_t n_plans = 0, n_early_plans = 0;        // statistics (pbf_dist_stats)
   uint32_t kept_nblk = 0;                         // tiles of the kept counts classify_count_kernel wrote into role_cnt (phase A -> phase C)
   uint32_t *h_pinned = nullptr;                   // plan steps: the two count matrices
   std::vector<uint64_t> last_counts;              // pbf_dist_advance_host: particles every rank returned last time
@@ -1527,7 +1528,11 @@ int group_step(std::vector<pbf_ctx *> &L, const pbf_params &p) {
       const int slot = (int)(d->step_index % D::kHotRing);
       PBF_CUDA(c, cudaMemcpyAsync(d->h_hot + slot, &d->dyn->hot, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       PBF_CUDA(c, cudaEventRecord(d->ev_step[slot], c->stream));
-      if (plan) d->last_plan_step = d->step_index;
+      if (plan) {
+        d->last_plan_step = d->step_index;
+        d->n_plans++;
+        if (hot) d->n_early_plans++;
+      }
     }
     c->have_state = true;
     c->prof.steps++;
@@ -1833,6 +1838,10 @@ int pbf_dist_stats_read(pbf_ctx *ctx, pbf_dist_stats *out) {
   if (!d->splits.empty()) { s.key_lo = d->splits[d->rank]; s.key_hi = d->splits[d->rank + 1]; }
   s.ghost_ring1 = h.n_ring1;
   s.boundary = h.n_boundary;
+  s.plan_steps = d->n_plans;
+  s.early_plans = d->n_early_plans;
+  s.capacity_owned = d->lay.cap_own;
+  s.capacity_ghosts = d->lay.cap_g;
   *out = s;
   return PBF_OK;
 }

@@ -187,3 +187,33 @@ def test_slab_group_advance_returns_the_mesh(gpu):
     assert nv == len(res.vs) and nv > 0
     assert np.array_equal(one["id"], many["id"])
     assert np.array_equal(res.vs.view(np.uint32), mesh.vs.view(np.uint32))
+
+
+def test_slab_group_replans_early_when_a_capacity_fills(gpu):
+    """No scheduled re-plan at all (pbf_dist_set_replan(0): the arenas are sized once, on the first step, from the block of
+    the dam break standing in its corner).  The dam then collapses across the tank: the owned and ghost counts of every key
+    range drift far from what the first plan sized for.  The ranks must notice from the count matrices (SlabDyn::hot),
+    re-plan together without talking, and stay bit-identical to one device."""
+    p, xs = scenes.dam_break(64, 3)  # 262 144 particles: the fixed slack of a capacity (4 096) is small beside a rank's share
+    frames = 90
+    with Solver(H, 0) as s:
+        s.upload(xs.copy())
+        for f in range(frames):
+            s.step(p)
+        ref = s.download()
+    with LocalGroup(H, [0] * 4) as g:
+        g.ranks[0].set_replan(0)
+        g.upload(xs.copy())
+        first = None
+        for f in range(frames):
+            g.step(p)
+            if f == 0:
+                first = [r.stats() for r in g.ranks]
+        got = g.download()
+        last = [r.stats() for r in g.ranks]
+    assert np.array_equal(ref["id"], got["id"])
+    assert np.array_equal(ref["position"].view(np.uint32), got["position"].view(np.uint32))
+    # the ranks re-planned although no re-plan was scheduled, all of them on the same steps
+    assert first[0]["plan_steps"] == 1 and first[0]["early_plans"] == 0
+    assert last[0]["early_plans"] >= 1, last
+    assert len({(s["plan_steps"], s["early_plans"]) for s in last}) == 1
