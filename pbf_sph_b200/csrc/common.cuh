@@ -366,6 +366,7 @@ int launch_finalise(pbf_ctx *ctx, const float4 *pstar, float4 *pos, float4 *vel)
 int launch_xsph_vorticity(pbf_ctx *ctx, const uint32_t *keys_sorted, const uint32_t *table, const float4 *pstar, float4 *vel,
                           float4 *scratch_omega, float4 *scratch_vel);
 int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *total_out_dev);
+int exclusive_scan_rows_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t row_len, uint32_t *totals_dev);
 int mc_run(pbf_ctx *ctx, const pbf_params &p, const uint32_t *table, const float4 *pos, const float4 *col);
 // the same in three parts (slab path: every rank evaluates the lattice points it owns into rank 0's lattice, rank 0 extracts)
 int mc_prepare(pbf_ctx *ctx, const pbf_params &p);

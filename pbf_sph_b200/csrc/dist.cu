@@ -164,7 +164,7 @@ struct pbf_dist_state {
   bool fresh = false;
   // device scratch
   SlabDyn *dyn = nullptr, *h_dyn = nullptr;       // device / pinned mirror (valid after a stream sync)
-  DevBuf<uint32_t> d_splits, d_row, d_hist, d_scratch;
+  DevBuf<uint32_t> d_splits, d_row, d_hist, d_scratch, row_tot;  // row_tot: totals of the row-wise scans (kMaxWorld words)
   DevBuf<uint32_t> mask, send_idx, leave_idx, blk_cnt, v2, role, role_cnt, ring1_idx, bnd_idx;
   DevBuf<float4> pstar1;
   bool diffuse_pending = false;
@@ -196,7 +196,7 @@ struct pbf_dist_state {
   void release() {
     release_arena();
     up_pos.release(); up_vel.release(); up_col.release(); up_ids.release();
-    d_splits.release(); d_row.release(); d_hist.release(); d_scratch.release();
+    d_splits.release(); d_row.release(); d_hist.release(); d_scratch.release(); row_tot.release();
     mask.release(); send_idx.release(); leave_idx.release(); blk_cnt.release(); v2.release(); role.release();
     role_cnt.release(); ring1_idx.release(); bnd_idx.release(); pstar1.release();
     if (dyn) cudaFree(dyn);
@@ -233,6 +233,20 @@ __device__ __forceinline__ int owner_of(const uint32_t *splits, int world, uint3
   return o;
 }
 
+// OR of `m` over the block (all threads get it).  Most tiles send nothing anywhere: the loops over the destinations below
+// run over the set bits of this only.
+__device__ __forceinline__ uint32_t block_or(uint32_t m) {
+  __shared__ uint32_t acc;
+  if (threadIdx.x == 0) acc = 0u;
+  __syncthreads();
+  const uint32_t w = __reduce_or_sync(0xFFFFFFFFu, m);
+  if ((threadIdx.x & 31u) == 0u && w) atomicOr(&acc, w);
+  __syncthreads();
+  const uint32_t r = acc;
+  __syncthreads();  // `acc` may be reset by the next call
+  return r;
+}
+
 // Destination of every held particle after predict_key: mask[i] = 1 << owner when the owner is another rank, else 0
 // (the same mask format as the ghost lists, so ghost_scatter_kernel builds the leave lists), and in the same pass the
 // per-tile counts the two compactions of the migration need: cnt[d * nblk + blk] = particles of the tile leaving for rank d
@@ -255,12 +269,13 @@ __global__ void classify_count_kernel(const uint32_t *__restrict__ keys, const u
   if (threadIdx.x == 0 && outside) atomicAdd(n_outside, (uint32_t)outside);
   const int stay = __syncthreads_count(i < n && m == 0u);
   if (threadIdx.x == 0) kept[blockIdx.x] = (uint32_t)stay;
-  const int leaving = __syncthreads_count(m != 0u);  // block-uniform: most tiles lose nobody
-  for (int d = 0; d < world; ++d) {
-    const int c = leaving ? __syncthreads_count((m >> d) & 1u) : 0;
+  if ((int)threadIdx.x < world) cnt[threadIdx.x * nblk + blockIdx.x] = 0u;
+  for (uint32_t todo = block_or(m); todo; todo &= todo - 1u) {  // most tiles lose nobody
+    const int d = __ffs(todo) - 1;
+    const int c = __syncthreads_count((m >> d) & 1u);
     if (threadIdx.x == 0) {
       cnt[(uint32_t)d * nblk + blockIdx.x] = (uint32_t)c;
-      if (c) atomicAdd(row + d, (uint32_t)c);
+      atomicAdd(row + d, (uint32_t)c);
     }
   }
 }
@@ -325,31 +340,47 @@ __global__ void ghost_count_kernel(const uint32_t *__restrict__ mask, const uint
   const uint32_t n = __ldg(n_dev);
   const uint32_t i = blockIdx.x * kBlk + threadIdx.x;
   const uint32_t m = i < n ? __ldg(mask + i) : 0u;
-  for (int d = 0; d < world; ++d) {
+  if ((int)threadIdx.x < world) cnt[threadIdx.x * nblk + blockIdx.x] = 0u;
+  for (uint32_t todo = block_or(m); todo; todo &= todo - 1u) {  // block_or's barriers order the zeroes before the counts
+    const int d = __ffs(todo) - 1;
     const int c = __syncthreads_count((m >> d) & 1u);
     if (threadIdx.x == 0) {
       cnt[(uint32_t)d * nblk + blockIdx.x] = (uint32_t)c;
-      if (c) atomicAdd(row + d, (uint32_t)c);
+      atomicAdd(row + d, (uint32_t)c);
     }
   }
 }
 
-// Stable scatter of the send lists: list[offs[d][blk] + rank within the tile] = i, destination-major.
+// Stable scatter of the send lists: list[start of destination d + offs[d][blk] + rank within the tile] = i,
+// destination-major.  offs = the per-destination rows of tile counts, each scanned on its own; row_tot[d] = row d's total.
 __global__ void ghost_scatter_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ n_dev, int world,
-                                     uint32_t nblk, const uint32_t *__restrict__ offs, uint32_t *__restrict__ list,
-                                     uint32_t list_cap) {
+                                     uint32_t nblk, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ row_tot,
+                                     uint32_t *__restrict__ list, uint32_t list_cap) {
   __shared__ uint32_t wsum[kBlk / 32];
+  __shared__ uint32_t row_base[kMaxWorld];
   const uint32_t n = __ldg(n_dev);
   if (blockIdx.x * kBlk >= n) return;
+  if (threadIdx.x < 32) {  // exclusive sums of the (at most 32) row totals
+    const uint32_t t = (int)threadIdx.x < world ? __ldg(row_tot + threadIdx.x) : 0u;
+    uint32_t incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if ((int)threadIdx.x >= o) incl += up;
+    }
+    row_base[threadIdx.x] = incl - t;
+  }
+  __syncthreads();
   const uint32_t i = blockIdx.x * kBlk + threadIdx.x;
   const uint32_t m = i < n ? __ldg(mask + i) : 0u;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int d = 0; d < world; ++d) {
+  for (uint32_t todo = block_or(m); todo; todo &= todo - 1u) {
+    const int d = __ffs(todo) - 1;
     const bool bit = (m >> d) & 1u;
     const unsigned b = __ballot_sync(0xFFFFFFFFu, bit);
     if (lane == 0) wsum[warp] = __popc(b);
     __syncthreads();
-    uint32_t base = __ldg(offs + (uint32_t)d * nblk + blockIdx.x);
+    uint32_t base = row_base[d] + __ldg(offs + (uint32_t)d * nblk + blockIdx.x);
     for (unsigned w = 0; w < warp; ++w) base += wsum[w];
     const uint32_t slot = base + __popc(b & ((1u << lane) - 1u));
     if (bit && slot < list_cap) list[slot] = i;
@@ -659,16 +690,16 @@ __global__ void roles_kernel(const uint32_t *__restrict__ keys, const uint32_t *
 }
 // the two lists (absolute indices, ascending) from the scanned tile counts; list k starts at offs[k * nblk]
 __global__ void role_lists_kernel(const uint32_t *__restrict__ role, SlabDyn *__restrict__ dyn, uint32_t nblk,
-                                  const uint32_t *__restrict__ offs, const uint32_t *__restrict__ total,
+                                  const uint32_t *__restrict__ offs, const uint32_t *__restrict__ row_tot,
                                   uint32_t *__restrict__ ring1, uint32_t *__restrict__ bnd, uint32_t cap_ring1,
                                   uint32_t cap_own) {
   __shared__ uint32_t wsum[kBlk / 32];
   const uint32_t t = blockIdx.x * kBlk + threadIdx.x;
   const uint32_t n_local = dyn->n_local;
   if (t == 0) {
-    const uint32_t r1 = offs[nblk] - offs[0];
+    const uint32_t r1 = __ldg(row_tot);
     dyn->n_ring1 = min(r1, cap_ring1);
-    dyn->n_boundary = min(__ldg(total) - offs[nblk], cap_own);
+    dyn->n_boundary = min(__ldg(row_tot + 1), cap_own);
     if (r1 > cap_ring1) atomicOr(&dyn->overflow, 2u);
   }
   if (blockIdx.x * kBlk >= n_local) return;
@@ -679,7 +710,7 @@ __global__ void role_lists_kernel(const uint32_t *__restrict__ role, SlabDyn *__
     const unsigned b = __ballot_sync(0xFFFFFFFFu, bit);
     if (lane == 0) wsum[warp] = __popc(b);
     __syncthreads();
-    uint32_t base = __ldg(offs + k * nblk + blockIdx.x) - __ldg(offs + k * nblk);
+    uint32_t base = __ldg(offs + k * nblk + blockIdx.x);  // the rows are scanned one by one
     for (unsigned w = 0; w < warp; ++w) base += wsum[w];
     const uint32_t slot = base + __popc(b & ((1u << lane) - 1u));
     uint32_t *out = k == 0 ? ring1 : bnd;
@@ -1066,8 +1097,8 @@ int phase_b(pbf_ctx *c) {
   PBF_LAUNCH_CHECK(c);
   if (W > 1) {
     const uint32_t nblk = d->cnt_nblk;  // as counted in phase A (a plan step may have grown the arena since)
-    PBF_TRY(exclusive_scan_u32(c, d->blk_cnt.p, d->blk_cnt.p, (uint64_t)W * nblk, nullptr));
-    ghost_scatter_kernel<<<nblk, kBlk, 0, c->stream>>>(d->mask.p, &d->dyn->n_in, W, nblk, d->blk_cnt.p, d->leave_idx.p, (uint32_t)d->leave_idx.cap);
+    PBF_TRY(exclusive_scan_rows_u32(c, d->blk_cnt.p, d->blk_cnt.p, (uint32_t)W, nblk, d->row_tot.p));
+    ghost_scatter_kernel<<<nblk, kBlk, 0, c->stream>>>(d->mask.p, &d->dyn->n_in, W, nblk, d->blk_cnt.p, d->row_tot.p, d->leave_idx.p, (uint32_t)d->leave_idx.cap);
     PBF_LAUNCH_CHECK(c);
     push_migrants_kernel<<<nblk, kBlk, 0, c->stream>>>(d->dyn, d->peers, l, c->cur, c->cur_col, W, d->leave_idx.p, c->pos[c->cur].p + l.own_off,
                                                        c->vel[c->cur].p + l.own_off, c->col[c->cur_col].p + l.own_off,
@@ -1132,8 +1163,8 @@ int phase_d(pbf_ctx *c) {
     PhaseScope ps(c, PBF_PH_HALO);
     if (W > 1) {
       const uint32_t oblk = d->cnt_nblk;  // as counted in phase C
-      PBF_TRY(exclusive_scan_u32(c, d->blk_cnt.p, d->blk_cnt.p, (uint64_t)W * oblk, nullptr));
-      ghost_scatter_kernel<<<oblk, kBlk, 0, c->stream>>>(d->mask.p, &d->dyn->n_own, W, oblk, d->blk_cnt.p, d->send_idx.p, (uint32_t)d->send_idx.cap);
+      PBF_TRY(exclusive_scan_rows_u32(c, d->blk_cnt.p, d->blk_cnt.p, (uint32_t)W, oblk, d->row_tot.p));
+      ghost_scatter_kernel<<<oblk, kBlk, 0, c->stream>>>(d->mask.p, &d->dyn->n_own, W, oblk, d->blk_cnt.p, d->row_tot.p, d->send_idx.p, (uint32_t)d->send_idx.cap);
       PBF_LAUNCH_CHECK(c);
       push_ghosts_kernel<<<div_up(d->send_idx.cap, kBlk), kBlk, 0, c->stream>>>(d->dyn, d->peers, l, oc, W, d->send_idx.p, c->pstar[0].p,
                                                                                 c->pos[o].p, c->col[oc].p, c->keys_sorted);
@@ -1166,8 +1197,8 @@ int phase_e(pbf_ctx *c) {
     roles_kernel<<<nblk, kBlk, 0, c->stream>>>(keys_local, d->mask.p, d->dyn, l, c->sc.G, d->splits[d->rank], d->splits[d->rank + 1], nblk,
                                                d->role.p, d->role_cnt.p);
     PBF_LAUNCH_CHECK(c);
-    PBF_TRY(exclusive_scan_u32(c, d->role_cnt.p, d->role_cnt.p, (uint64_t)2 * nblk, c->mc_total_dev + 1));
-    role_lists_kernel<<<nblk, kBlk, 0, c->stream>>>(d->role.p, d->dyn, nblk, d->role_cnt.p, c->mc_total_dev + 1, d->ring1_idx.p, d->bnd_idx.p,
+    PBF_TRY(exclusive_scan_rows_u32(c, d->role_cnt.p, d->role_cnt.p, 2u, nblk, d->row_tot.p));
+    role_lists_kernel<<<nblk, kBlk, 0, c->stream>>>(d->role.p, d->dyn, nblk, d->role_cnt.p, d->row_tot.p, d->ring1_idx.p, d->bnd_idx.p,
                                                     2u * l.cap_g, l.cap_own);
     PBF_LAUNCH_CHECK(c);
   }
@@ -1567,6 +1598,7 @@ int dist_alloc(pbf_ctx *c, int rank, int world) {
   PBF_CUDA(c, cudaSetDevice(c->device));
   PBF_CUDA(c, d->d_splits.reserve(world + 2));
   PBF_CUDA(c, d->d_row.reserve(world + 4));
+  PBF_CUDA(c, d->row_tot.reserve(kMaxWorld));
   PBF_CUDA(c, d->d_scratch.reserve((size_t)16 * (world + 1) + 64));
   PBF_CUDA(c, cudaMalloc(&d->dyn, sizeof(SlabDyn)));
   PBF_CUDA(c, cudaMemset(d->dyn, 0, sizeof(SlabDyn)));

@@ -96,9 +96,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_apply_kernel(const uin
 // 18 us for 16 K entries with the serial tile walk before that.  `out` may alias `in`.
 constexpr int kScanWide = 1024;
 constexpr uint64_t kScanSmall = 128ull * 1024;
+// Launched with several blocks it scans ROWS: block r scans entries [r * n, (r + 1) * n) on their own and writes the row's
+// total to total_out[r] (exclusive_scan_rows_u32: the slab path's per-destination tile counts).
 __global__ void __launch_bounds__(kScanWide) scan_one_block_kernel(const uint32_t *in, uint32_t n, uint32_t *out,
                                                                    uint32_t *total_out) {
   __shared__ uint32_t wbase[kScanWide / 32];
+  in += (size_t)blockIdx.x * n;
+  out += (size_t)blockIdx.x * n;
+  if (total_out) total_out += blockIdx.x;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t seg = (((n + 31u) / 32u) + 127u) & ~127u;  // entries per warp, a multiple of the 128-entry stride
   const uint32_t lo = min(n, warp * seg), hi = min(n, lo + seg);
@@ -305,6 +310,19 @@ int exclusive_scan_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t
     PBF_LAUNCH_CHECK(ctx);
   }
   scan_tile_apply_kernel<<<(unsigned)t1, kScanThreads, 0, ctx->stream>>>(in, n, s1, out, total_out_dev);
+  PBF_LAUNCH_CHECK(ctx);
+  return PBF_OK;
+}
+
+// `rows` independent exclusive scans of row_len entries each, in place or not; totals[r] (device) = sum of row r.
+int exclusive_scan_rows_u32(pbf_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t rows, uint32_t row_len, uint32_t *totals_dev) {
+  if (rows == 0 || row_len == 0) return PBF_OK;
+  if (row_len > kScanSmall) {  // very long rows (> 33 M particles of capacity per rank): one general scan per row
+    for (uint32_t r = 0; r < rows; ++r)
+      PBF_TRY(exclusive_scan_u32(ctx, in + (size_t)r * row_len, out + (size_t)r * row_len, row_len, totals_dev ? totals_dev + r : nullptr));
+    return PBF_OK;
+  }
+  scan_one_block_kernel<<<rows, kScanWide, 0, ctx->stream>>>(in, row_len, out, totals_dev);
   PBF_LAUNCH_CHECK(ctx);
   return PBF_OK;
 }
