@@ -285,7 +285,7 @@ def roofline_of(prof, n, iters, steps):
             "note": "the neighbour passes are bound by the latency of their gathers, the L1 data pipe and instruction issue "
                     "(~195 candidate pairs per particle, one 16-byte position through L1 per pair and lane), not by HBM; "
                     "`issue` is the fraction of the warp-instruction issue slots; see DESIGN.md §4 and "
-                    "profiles/r01c_search_experiments.txt", "ms_per_step_by_family": breakdown,
+                    "profiles/r01c_search_experiments.txt, r02b_block_size.txt, r02c_list_layout.txt", "ms_per_step_by_family": breakdown,
             "achieved_GBps_by_family": per_kernel}
 
 
