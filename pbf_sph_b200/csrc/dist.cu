@@ -1122,7 +1122,9 @@ int phase_c(pbf_ctx *c) {
     PhaseScope ps(c, PBF_PH_HALO);
     // kept = mask 0, in input order: per-tile counts from phase A (role_cnt), scanned here, scattered into the merge input
     PBF_TRY(exclusive_scan_u32(c, d->role_cnt.p, d->role_cnt.p, nblk, nullptr));
-    merge_scatter_kernel<<<nblk, kBlk, 0, c->stream>>>(d->dyn, d->mask.p, d->role_cnt.p, c->key_in.p, k2, d->v2.p);
+    // the grid covers the CURRENT capacity: after a re-grow in this step the arrivals may reach beyond the tiles phase A
+    // counted (those extra tiles hold no kept particle and read no offset)
+    merge_scatter_kernel<<<std::max(nblk, div_up(n_cap, kBlk)), kBlk, 0, c->stream>>>(d->dyn, d->mask.p, d->role_cnt.p, c->key_in.p, k2, d->v2.p);
     PBF_LAUNCH_CHECK(c);
   }
   PBF_TRY(radix_sort_pairs(c, k2, n_cap, d->v2.p, &d->dyn->n_own));
