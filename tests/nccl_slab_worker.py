@@ -30,6 +30,14 @@ def main():
     sr.upload(shard(xs, rank, world))
     for f in range(frames):
         sr.step(scenes.apply_motion(p, f))
+    # ... and two more frames with the marching-cubes surface: every rank fills its lattice points into rank 0's arena
+    meshes = []
+    for f in range(frames, frames + 2):
+        pf = scenes.apply_motion(p, f)
+        pf.surface_enabled = 1
+        sr.step(pf)
+        if rank == 0:
+            meshes.append(sr.s.mesh())
     mine = sr.download()
     st = sr.stats()
     parts = [None] * world
@@ -41,10 +49,19 @@ def main():
             s.upload(xs)
             for f in range(frames):
                 s.step(scenes.apply_motion(p, f))
+            ref_meshes = []
+            for f in range(frames, frames + 2):
+                pf = scenes.apply_motion(p, f)
+                pf.surface_enabled = 1
+                s.step(pf)
+                ref_meshes.append(s.mesh())
             ref = s.download()
         ok = (len(ref) == len(got) and np.array_equal(ref["id"], got["id"])
               and all(np.array_equal(ref[k].view(np.uint32), got[k].view(np.uint32)) for k in ("position", "velocity", "colour")))
         ok = ok and sum(s_["ghosts"] for _, s_ in parts) > 0 and all(s_["owned"] > 0 for _, s_ in parts)
+        for a, b in zip(ref_meshes, meshes):  # the slab mesh is the single-device mesh, bit for bit
+            ok = ok and len(a.vs) > 0 and len(a.vs) == len(b.vs) and all(
+                np.array_equal(getattr(a, k).view(np.uint32), getattr(b, k).view(np.uint32)) for k in ("vs", "ns", "cs"))
         print("NCCL_SLAB_OK" if ok else "NCCL_SLAB_MISMATCH", [s_["owned"] for _, s_ in parts], flush=True)
     sr.close()
     dist.destroy_process_group()

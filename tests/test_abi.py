@@ -29,6 +29,35 @@ def test_struct_layouts():
     assert C.sizeof(capi.Params) == 80 and C.sizeof(capi.McParams) == 16
 
 
+def test_ctypes_mirrors_match_the_header(tmp_path):
+    """Every struct of include/pbf_cuda.h that crosses the boundary has the size and field offsets of its ctypes mirror
+    (compiled as plain C: the header is the contract a cgo / JNI / ctypes binding reads)."""
+    import subprocess
+    pairs = {"pbf_params": capi.Params, "pbf_mc_params": capi.McParams, "pbf_dist_stats": capi.DistStats,
+             "pbf_profile": capi.Profile, "pbf_well": capi.Well, "pbf_source": capi.Source, "pbf_drain": capi.Drain,
+             "pbf_query": capi.Query, "pbf_grid_info": capi.GridInfo}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pbf_cuda.h"', "int main(void) {"]
+    for cname, mirror in pairs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  printf("PH %d %d %d\\n", PBF_PH_HALO, PBF_PH_SLAB_ITERATIONS, PBF_PH_COUNT);', "  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    for line, (cname, mirror) in zip(out, pairs.items()):
+        got = line.split()
+        assert got[0] == cname
+        want = [C.sizeof(mirror)] + [getattr(mirror, f).offset for f, _ in mirror._fields_]
+        assert [int(v) for v in got[1:]] == want, (cname, got[1:], want)
+    ph = out[len(pairs)].split()
+    assert ph[0] == "PH" and int(ph[1]) == capi.PHASES.index("halo") and int(ph[2]) == capi.PHASES.index("slab_iterations")
+    assert int(ph[3]) == capi.PH_COUNT == len(capi.PHASES)
+
+
 def test_no_gpu_fails_loudly():
     L = capi.lib()
     ctx = C.c_void_p()
