@@ -342,9 +342,6 @@ int pbf_create(pbf_ctx **out, float h, int device) {
   ctx->h = h;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-#ifdef PBF_L2_GRAN
-  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, PBF_L2_GRAN);
-#endif
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);

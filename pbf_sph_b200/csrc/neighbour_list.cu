@@ -50,6 +50,8 @@ __device__ __forceinline__ uint32_t list_base(uint32_t a, uint32_t chunk_words) 
   return (a >> kChunkLog2) * chunk_words + (a & (kChunk - 1u));
 }
 
+// Cache policy of the list's stores / loads (streaming: written once, read once per pass).  The -D switches exist for the
+// A/B libraries of profiles/tools/build_variant.sh; .cg, L1::no_allocate and the default policy all measured within 1.5 %.
 #ifndef PBF_NL_ST
 #define PBF_NL_ST ".cs"
 #endif
@@ -57,23 +59,9 @@ __device__ __forceinline__ uint32_t list_base(uint32_t a, uint32_t chunk_words) 
 #define PBF_NL_LDQ ".cs"
 #endif
 
-// Candidate-position gather of the search loop.  PBF_NL_PF (64 / 128 / 256): L2 prefetch-size hint — a miss brings the
-// whole 128-byte line (eight positions of the same run) from DRAM instead of one 32-byte sector.
-__device__ __forceinline__ float4 ldg4s(const float4 *p) {
-#ifdef PBF_NL_GQ  /* cache qualifiers of the gather, e.g. ".nc.L1::evict_last" */
-  float4 v;
-  asm("ld.global" PBF_NL_GQ ".v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-#elif defined(PBF_NL_PF)
-#define PBF_STR2(x) #x
-#define PBF_STR(x) PBF_STR2(x)
-  float4 v;
-  asm("ld.global.nc.L2::" PBF_STR(PBF_NL_PF) "B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-#else
-  return __ldg(p);
-#endif
-}
+// Candidate-position gather of the search loop.  (L2 prefetch-size hints, L1 eviction priorities and coherent loads on this
+// gather were all measured in round 2 and changed nothing: profiles/r02b_block_size.txt, section 2.)
+__device__ __forceinline__ float4 ldg4s(const float4 *p) { return __ldg(p); }
 
 // list entry load (coherent — never .nc: the lambda kernel reads what it wrote itself)
 __device__ __forceinline__ uint32_t ld_list(const uint32_t *p) {
@@ -107,7 +95,7 @@ __device__ __forceinline__ void append_if(uint32_t *nl, uint32_t &slot, uint32_t
 // then kW position gathers in flight), then ONE masked batch for the 1..kW-1 hits left over — a scalar remainder loop
 // waits out two dependent latencies (list entry, then position) per hit.  kW = 8 in the delta pass; 4 in the lambda
 // pass, whose search loop needs the registers (56 -> 9 blocks per SM).
-template <int kW, bool kSameKernel, typename Acc>
+template <int kW, typename Acc>
 __device__ __forceinline__ void sum_over_hits(Acc &acc, const StepConst &c, const float4 pa, const float4 *__restrict__ pstar,
                                               const uint32_t *row, uint32_t k, uint32_t self) {
   uint32_t i = 0;
@@ -232,7 +220,7 @@ __device__ __forceinline__ void lambda_particle(const StepConst &c, const uint32
   acc.init();
   acc.set_mass(mass);
   if (k <= (uint32_t)kCap) {
-    sum_over_hits<4, true>(acc, c, pa, pstar_in, nl + base, k, a);
+    sum_over_hits<4>(acc, c, pa, pstar_in, nl + base, k, a);
   } else {
     for_each_candidate(key, c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
@@ -267,7 +255,7 @@ __device__ __forceinline__ void delta_particle(const StepConst &c, const uint32_
   DeltaAcc<kStrict> acc;
   acc.init();
   if (k <= (uint32_t)kCap) {
-    sum_over_hits<8, false>(acc, c, pa, pstar_in, nl + list_base(a, chunk_words), k, a);  // add_in skips the particle itself (r < EPSILON)
+    sum_over_hits<8>(acc, c, pa, pstar_in, nl + list_base(a, chunk_words), k, a);  // add_in skips the particle itself (r < EPSILON)
   } else {
     for_each_candidate(__ldg(keys + a), c.G, table, [&](uint32_t b) { acc.add(c, pa, ldg4(pstar_in + b)); });
   }
