@@ -9,9 +9,10 @@
 // in one arena that all peers map: directly inside one process, through CUDA IPC between processes), followed by a
 // cross-rank barrier on the stream.  All counts — migrants, owned particles, ghosts, send lists — stay in device
 // memory (`SlabDyn`); kernels read them there and grids are sized by the arena's capacities, so an ordinary step
-// never waits for the host: the host runs a step ahead and launch latency disappears behind the solver kernels.  The
-// host synchronises only on PLAN steps (after an upload and every `replan` steps), where it re-plans the key splits from
-// a global key histogram and re-sizes the arenas from the exact counts.
+// never waits for the host: the host runs up to two steps ahead and launch latency disappears behind the solver kernels.
+// The host synchronises only on PLAN steps (after an upload, every `replan` steps, and EARLY when some rank has filled a
+// capacity beyond its watermark — every rank derives that verdict from the count matrices, SlabDyn::hot), where it
+// re-plans the key splits from a global key histogram and re-sizes the arenas from the exact counts.
 //
 //   A  predict_key on the held particles; (plan steps) global key histogram -> new splits;
 //      classify every particle by the rank owning its key; count row -> every peer          [barrier 1]
@@ -24,15 +25,19 @@
 //   D  reorder (gather + predict) into the local arrays [ghosts below | owned | ghosts above] — globally key-sorted
 //      because ranks own ascending key ranges; the owned block starts at a FIXED offset; PUSH the ghost payload
 //      (pStar|mass, colour, key) into the destination's local arrays                        [barrier 4]
-//   E  cell table over the local array, roles -> compact lists (ring-1 ghosts, boundary, interior), diffuse on the owned
-//      cell blocks (side stream); per iteration: lambda on owned + ring-1 ghosts, delta on the boundary list, PUSH of the
-//      boundary pStar (16 B per ghost) into the destination's halo inbox on the comm stream ‖ delta on the interior
-//      list [barrier per iteration], inbox -> ghost slots; finally finalise (owned).
+//   E  cell table over the local array, roles -> compact lists (ring-1 ghosts, boundary), diffuse on the owned cell blocks
+//      (side stream); per iteration: lambda on owned + ring-1 ghosts, then side by side: delta on the interior in place
+//      (boundary particles skipped by mask) ‖ on the high-priority comm stream delta on the boundary list, PUSH of the
+//      boundary pStar (16 B per ghost) into the destination's halo inbox, barrier; inbox -> ghost slots; finally
+//      finalise (owned).
+//   F  (params.surface_enabled) marching cubes: final positions + diffused colours of the send list -> the destinations'
+//      ghost slots [two barriers]; every rank evaluates the lattice points whose cell it owns into RANK 0's lattice
+//      [barrier]; rank 0 counts, scans, emits.
 //
-// Transports: NCCL (one process per GPU; NCCL carries the arena handles, the plan-step reductions and the barriers — a
-// one-word all-reduce on the stream; the data itself moves by peer stores) and LOCAL (every rank is a context of this
-// process; barriers are CUDA events between the ranks' streams — this is what the 1-GPU parity tests and the
-// multi-device sph::Solver drive).  Uploads are collective: every rank uploads between the same two steps.
+// Groups: NCCL (one process per GPU; NCCL carries the arena handles and the plan-step reductions; the data moves by peer
+// stores and the barriers are a flag kernel over peer memory) and LOCAL (every rank is a context of this process;
+// barriers are CUDA events between the ranks' streams — this is what the 1-GPU parity tests and the multi-device
+// sph::Solver drive).  Uploads are collective: every rank uploads between the same two steps.
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only; the symbols are resolved with dlsym
 
